@@ -1,0 +1,145 @@
+// swr/detail/common.h -- record layouts, kernel argument blocks and exact-fp32 helpers shared by
+// the geometry kernel (geometry.cuh), the tile kernel (tile.cuh) and the runtime (runtime.cu).
+//
+// HBM layout of one pass (up to `maxPrims` input primitives, R = record index):
+//   bbox   [R]  4 x int16  inclusive pixel bounds of the primitive's fragment footprint
+//                         (min > max  <=>  dead: clipped away, culled, zero area, off-screen)
+//   gbox   [R/32] 4 x int16 union of the 32 records of one group (one warp of the geometry kernel)
+//   head   [R]  3 x float4 edge equations / line start+step / point position, flags, ordinal
+//   params [R]  paramStride floats: interpolation planes (a,b,c) in the order z?, invw?, avar[], pvar[]
+//               (lines: (start, step) pairs; points: values)
+//   span   [R]  3 x float4 (Span / Adaptive only) the two scan-converted halves
+//   tilemap[tile][chunk/32] one bit per (screen tile, chunk): chunk may touch the tile
+// Records [0, maxPrims) are the "original slots" (record = primitive index within the pass, so
+// record order is submission order); clipper fan extras of batch b live in a bump-allocated,
+// 32-aligned range extra[b] = {base, count} behind them.  Chunk 2b = original slots of batch b,
+// chunk 2b+1 = its extras: ascending chunk id, then ascending record, is exactly the reference's
+// emission order (VertexProcessor.cpp:252-261, Rasterizer.h:134-141).
+#pragma once
+
+#include <stdint.h>
+#include "../../swr_b200.h"
+
+#if defined(__CUDACC__)
+#define SWR_HD __host__ __device__ __forceinline__
+#define SWR_D __device__ __forceinline__
+#else
+#define SWR_HD inline
+#define SWR_D inline
+#endif
+
+namespace swr {
+namespace detail {
+
+constexpr int kBatch = SWR_BATCH_PRIMS;          // 1024 input primitives (VertexProcessor.cpp:110)
+constexpr int kGroup = 32;                       // records per group AABB
+constexpr int kMaxPoly = SWR_MAX_POLY;
+constexpr int kMaxFan = kMaxPoly - 2;            // triangles per clipped input triangle
+constexpr int kGeomThreads = 256;
+constexpr int kTileThreads = 256;
+
+// ---- exact fp32: never contracted into FMA, whatever flags the including TU is built with ----
+#if defined(__CUDA_ARCH__)
+SWR_HD float fmul(float a, float b) { return __fmul_rn(a, b); }
+SWR_HD float fadd(float a, float b) { return __fadd_rn(a, b); }
+SWR_HD float fsub(float a, float b) { return __fsub_rn(a, b); }
+SWR_HD float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+SWR_HD int f2i(float a) { return __float2int_rz(a); }
+SWR_HD float i2f(int a) { return __int2float_rn(a); }
+#else
+// Host build (tests/hostcheck only): compile with -ffp-contract=off.
+SWR_HD float fmul(float a, float b) { return a * b; }
+SWR_HD float fadd(float a, float b) { return a + b; }
+SWR_HD float fsub(float a, float b) { return a - b; }
+SWR_HD float fdiv(float a, float b) { return a / b; }
+SWR_HD int f2i(float a) { return (int)a; }
+SWR_HD float i2f(int a) { return (float)a; }
+#endif
+
+struct Box16 { int16_t x0, y0, x1, y1; };        // inclusive; dead when x0 > x1
+SWR_HD Box16 deadBox() { Box16 b; b.x0 = 32767; b.y0 = 32767; b.x1 = -32768; b.y1 = -32768; return b; }
+
+// head flags
+enum : uint32_t {
+    kTie0 = 1u, kTie1 = 2u, kTie2 = 4u,          // EdgeEquation::tie of e0, e1, e2
+    kModeSpan = 8u,                               // this triangle is scan-converted (Span, or Adaptive's choice)
+};
+
+struct RenderTargetDesc { void *ptr; int32_t pitch; int32_t pad; };
+
+// Arguments of the geometry kernel (one launch = one pass).
+struct GeomArgs {
+    // input
+    const int32_t *indices;          // first index of the pass
+    int32_t numPrims;                // primitives in this pass
+    uint32_t firstBatch;             // global batch index of the pass's first batch (ordinals)
+    int32_t drawMode;
+    const void *attribPtr[SWR_MAX_VERTEX_ATTRIBS];
+    int32_t attribStride[SWR_MAX_VERTEX_ATTRIBS];
+    // raster-list entry (IRasterizer::draw*List): when rasterVerts != nullptr the vertex shader,
+    // clipping, transform and culling are skipped and 144-byte RasterizerVertex records are read
+    const void *rasterVerts;
+    // fixed-function state
+    float px, py, ox, oy;            // VertexProcessor.cpp:50-53
+    float depthN, depthF;
+    int32_t cullMode, rasterMode;
+    int32_t scMinX, scMinY, scMaxX, scMaxY;   // Rasterizer.h:81-87 (max exclusive)
+    // what the pixel shader interpolates (TriangleEquations uses the PIXEL shader's counts)
+    int32_t nA, nP, useZ, useW;
+    // output
+    Box16 *bbox;
+    Box16 *gbox;
+    float4 *head;
+    float *params;
+    float4 *span;
+    int32_t paramStride;
+    uint32_t *tilemap;
+    int32_t chunkWords;              // 32-bit words per tilemap row
+    int32_t tileShift;               // log2(tile size in pixels)
+    int32_t tilesX, tilesY;
+    uint2 *extra;                    // per batch {base, count}
+    uint32_t *extraAlloc;            // bump allocator cursor (record index), starts at extrasBegin
+    uint32_t extrasEnd;              // capacity end (record index)
+    uint32_t *errorFlag;
+    float *dbgVerts;                 // optional: 12 floats per record (3 x xyzw, screen space)
+};
+
+// Arguments of the tile kernel.
+struct TileArgs {
+    const Box16 *bbox;
+    const Box16 *gbox;
+    const float4 *head;
+    const float *params;
+    const float4 *span;
+    int32_t paramStride;
+    const uint32_t *tilemap;
+    int32_t chunkWords;
+    int32_t numChunks;               // 2 * batches in the pass
+    int32_t numPrims;
+    const uint2 *extra;
+    int32_t tilesX, tilesY;
+    int32_t rank, world;             // sort-first ownership: (tx + 3*ty) % world == rank
+    int32_t rtWidth, rtHeight;
+    int32_t numRT;
+    RenderTargetDesc rt[SWR_MAX_RENDER_TARGETS];
+    int32_t scMinX, scMinY, scMaxX, scMaxY;
+    unsigned long long *fragCounter;
+    const uint32_t *errorFlag;
+};
+
+// number of floats of one params record
+SWR_HD int paramFloats(int drawMode, int nA, int nP, int useZ, int useW)
+{
+    if (drawMode == SWR_DRAW_TRIANGLE) {
+        int planes = (useZ ? 1 : 0) + ((useW || nP > 0) ? 1 : 0) + nA + nP;
+        return ((planes * 3) + 3) & ~3;
+    }
+    int vars = (useZ ? 1 : 0) + (useW ? 1 : 0) + nA + nP;
+    int n = drawMode == SWR_DRAW_LINE ? vars * 2 : vars;
+    return (n + 3) & ~3;
+}
+
+SWR_HD bool tileOwned(int tx, int ty, int rank, int world) { return world <= 1 || ((tx + 3 * ty) % world) == rank; }
+
+} // namespace detail
+} // namespace swr

@@ -1,0 +1,669 @@
+// swr/detail/geometry.cuh -- the geometry kernel (K1+K2+K3 of SURVEY.md 2.3), templated on the
+// user's vertex shader so processVertex is inlined.
+//
+// One CTA = one reference batch of 1024 input primitives (VertexProcessor.cpp:110-116), one
+// thread = one primitive at a time (4 rounds of 256).  Per primitive, as a pure function:
+//   fetch indices -> VS::processVertex per corner (VertexProcessor.cpp:97-105,134-150)
+//   -> clip mask (VertexProcessor.cpp:122-132) -> Sutherland-Hodgman against the flagged planes in
+//   the fixed order +X,-X,+Y,-Y,+Z,-Z (PolyClipper.cpp:45-81) or the parametric line clip
+//   (LineClipper.cpp:30-56) -> perspective divide + viewport + depth range
+//   (VertexProcessor.cpp:347-377) -> cull / re-orient (VertexProcessor.cpp:319-345)
+//   -> TriangleEquations setup (TriangleEquations.h:47-71) + footprint box -> record in HBM.
+// The reference's 16-entry VertexCache only avoids re-shading (results are identical without
+// it); here the three corner fetches of neighbouring primitives hit L1/L2.
+// All parity-critical arithmetic goes through fmul/fadd/fsub/fdiv (never contracted).
+#pragma once
+
+#include "common.h"
+#include "../VertexShaderBase.h"
+#include "../ParameterEquation.h"
+#include "../Uniforms.h"
+
+namespace swr {
+namespace detail {
+
+template <int NA, int NP>
+struct CVert {
+    float x, y, z, w;
+    float a[NA > 0 ? NA : 1];
+    float p[NP > 0 ? NP : 1];
+};
+
+// VertexProcessor.cpp:122-132 -- strict '<' on w-x, x+w, ...
+SWR_HD int outcode(float x, float y, float z, float w)
+{
+    int m = 0;
+    if (fsub(w, x) < 0) m |= 0x01;
+    if (fadd(x, w) < 0) m |= 0x02;
+    if (fsub(w, y) < 0) m |= 0x04;
+    if (fadd(y, w) < 0) m |= 0x08;
+    if (fsub(w, z) < 0) m |= 0x10;
+    if (fadd(z, w) < 0) m |= 0x20;
+    return m;
+}
+
+// a*x + b*y + c*z + d*w, left to right, with the literal plane coefficients of
+// VertexProcessor.cpp:187-192 / 237-242 (PolyClipper.cpp:56,62, LineClipper.cpp:35-36).
+SWR_HD float planeDist(int plane, float x, float y, float z, float w)
+{
+    float a = 0.0f, b = 0.0f, c = 0.0f;
+    const float d = 1.0f;
+    switch (plane) {
+    case 0: a = -1.0f; break;
+    case 1: a = 1.0f; break;
+    case 2: b = -1.0f; break;
+    case 3: b = 1.0f; break;
+    case 4: c = -1.0f; break;
+    default: c = 1.0f; break;
+    }
+    return fadd(fadd(fadd(fmul(a, x), fmul(b, y)), fmul(c, z)), fmul(d, w));
+}
+
+// PolyClipper.h:34-48 -- v0*(1-t) + v1*t on x,y,z,w and the VERTEX shader's variable counts.
+template <int NA, int NP>
+SWR_HD void lerpVert(CVert<NA, NP> &o, const CVert<NA, NP> &v0, const CVert<NA, NP> &v1, float t)
+{
+    const float s = fsub(1.0f, t);
+    o.x = fadd(fmul(v0.x, s), fmul(v1.x, t));
+    o.y = fadd(fmul(v0.y, s), fmul(v1.y, t));
+    o.z = fadd(fmul(v0.z, s), fmul(v1.z, t));
+    o.w = fadd(fmul(v0.w, s), fmul(v1.w, t));
+#pragma unroll
+    for (int i = 0; i < NA; ++i) o.a[i] = fadd(fmul(v0.a[i], s), fmul(v1.a[i], t));
+#pragma unroll
+    for (int i = 0; i < NP; ++i) o.p[i] = fadd(fmul(v0.p[i], s), fmul(v1.p[i], t));
+}
+
+SWR_HD int sgn3(float v) { return (0.0f < v) - (v < 0.0f); }   // PolyClipper.h:91-94
+
+// One Sutherland-Hodgman pass (PolyClipper.cpp:45-81).  Returns the new vertex count; -1 when
+// the polygon would exceed kMaxPoly.
+template <int NA, int NP>
+SWR_HD int clipPolyPlane(const CVert<NA, NP> *in, int n, CVert<NA, NP> *out, int plane)
+{
+    int m = 0;
+    int iprev = 0;
+    float dprev = planeDist(plane, in[0].x, in[0].y, in[0].z, in[0].w);
+    for (int i = 1; i <= n; ++i) {
+        const int icur = (i == n) ? 0 : i;
+        const float d = planeDist(plane, in[icur].x, in[icur].y, in[icur].z, in[icur].w);
+        if (dprev >= 0) {
+            if (m >= kMaxPoly) return -1;
+            out[m++] = in[iprev];
+        }
+        if (sgn3(d) != sgn3(dprev)) {
+            const float t = d < 0 ? fdiv(dprev, fsub(dprev, d)) : fdiv(-dprev, fsub(d, dprev));
+            if (m >= kMaxPoly) return -1;
+            lerpVert(out[m++], in[iprev], in[icur], t);
+        }
+        iprev = icur;
+        dprev = d;
+    }
+    return m;
+}
+
+// Clip a triangle against the planes flagged in `mask`.  bufA holds the 3 input vertices; the
+// result is in *res (bufA or bufB).  Returns the polygon size (0 when fully clipped / overflow).
+template <int NA, int NP>
+SWR_HD int clipTriangle(CVert<NA, NP> *bufA, CVert<NA, NP> *bufB, int mask, CVert<NA, NP> **res)
+{
+    CVert<NA, NP> *in = bufA, *out = bufB;
+    int n = 3;
+    for (int pl = 0; pl < 6; ++pl) {
+        if (!(mask & (1 << pl))) continue;
+        if (n < 3) break;                                   // PolyClipper.cpp:47-48
+        n = clipPolyPlane(in, n, out, pl);
+        if (n < 0) { n = 0; break; }
+        CVert<NA, NP> *t = in; in = out; out = t;
+    }
+    *res = in;
+    return n < 3 ? 0 : n;                                   // VertexProcessor.cpp:244-250
+}
+
+// VertexProcessor.cpp:347-377 -- perspective divide, viewport (y flipped), depth range.  w stays.
+template <int NA, int NP>
+SWR_HD void toScreen(const GeomArgs &g, CVert<NA, NP> &v)
+{
+    const float invW = fdiv(1.0f, v.w);
+    v.x = fmul(v.x, invW);
+    v.y = fmul(v.y, invW);
+    v.z = fmul(v.z, invW);
+    v.x = fadd(fmul(g.px, v.x), g.ox);
+    v.y = fadd(fmul(g.py, -v.y), g.oy);
+    v.z = fadd(fmul(fmul(0.5f, fsub(g.depthF, g.depthN)), v.z), fmul(0.5f, fadd(g.depthN, g.depthF)));
+}
+
+SWR_HD float min3f(float a, float b, float c) { float m = b < a ? b : a; return c < m ? c : m; }   // std::min nesting
+SWR_HD float max3f(float a, float b, float c) { float m = a < b ? b : a; return m < c ? c : m; }   // std::max nesting
+SWR_HD int imin(int a, int b) { return a < b ? a : b; }
+SWR_HD int imax(int a, int b) { return a > b ? a : b; }
+SWR_HD int16_t clamp16(int v) { return (int16_t)imin(imax(v, -32768), 32767); }
+
+SWR_HD Box16 makeBox(int x0, int y0, int x1, int y1)
+{
+    // clamp to the addressable screen; empty after clamping => dead
+    x0 = imax(x0, 0); y0 = imax(y0, 0);
+    x1 = imin(x1, 32767); y1 = imin(y1, 32767);
+    if (x0 > x1 || y0 > y1) return deadBox();
+    Box16 b; b.x0 = (int16_t)x0; b.y0 = (int16_t)y0; b.x1 = (int16_t)x1; b.y1 = (int16_t)y1;
+    return b;
+}
+
+// One scan-converted half of a triangle (Rasterizer.h:360-411): rows [y0, y1), per row
+// x = (vx + inv * dy) + 0.5 with dy = (row - vy) + 0.5.
+struct SpanHalf { float vx, vy, inv1, inv2; int y0, y1; };
+
+SWR_HD float spanX(float vx, float vy, float inv, int row)
+{
+    const float dy = fadd(fsub(i2f(row), vy), 0.5f);
+    return fadd(fadd(vx, fmul(inv, dy)), 0.5f);
+}
+
+// Rasterizer.h:318-358: sort by y, split at the middle vertex, left/right by x.
+SWR_HD void spanSetup(float x0, float y0, float x1, float y1, float x2, float y2, SpanHalf &bot, SpanHalf &top)
+{
+    float tx = x0, ty = y0, mx = x1, my = y1, bx = x2, by = y2, f;
+    if (ty > my) { f = tx; tx = mx; mx = f; f = ty; ty = my; my = f; }
+    if (my > by) { f = mx; mx = bx; bx = f; f = my; my = by; by = f; }
+    if (ty > my) { f = tx; tx = mx; mx = f; f = ty; ty = my; my = f; }
+    const float dy = fsub(by, ty);
+    const float iy = fsub(my, ty);
+    bot.vx = bot.vy = bot.inv1 = bot.inv2 = 0.0f; bot.y0 = bot.y1 = 0;
+    top = bot;
+    float lx, ly, rx, ry;
+    bool hasBot = true, hasTop = true;
+    if (my == ty) {                      // flat top: l = m, r = t (Rasterizer.h:330-335)
+        lx = mx; ly = my; rx = tx; ry = ty;
+        hasBot = false;
+    } else if (my == by) {               // flat bottom: l = m, r = b (Rasterizer.h:336-341)
+        lx = mx; ly = my; rx = bx; ry = by;
+        hasTop = false;
+    } else {                             // general: split vertex v4 on the long edge (Rasterizer.h:344-350)
+        lx = mx; ly = my;
+        ry = my;
+        rx = fadd(tx, fmul(fdiv(fsub(bx, tx), dy), iy));
+    }
+    if (lx > rx) { f = lx; lx = rx; rx = f; f = ly; ly = ry; ry = f; }
+    if (hasBot) {                        // drawBottomFlatTriangle(eqn, t, l, r)  (Rasterizer.h:360-385)
+        bot.vx = tx; bot.vy = ty;
+        bot.inv1 = fdiv(fsub(lx, tx), fsub(ly, ty));
+        bot.inv2 = fdiv(fsub(rx, tx), fsub(ry, ty));
+        bot.y0 = f2i(fadd(ty, 0.5f));
+        bot.y1 = f2i(fadd(ly, 0.5f));
+    }
+    if (hasTop) {                        // drawTopFlatTriangle(eqn, l, r, b)  (Rasterizer.h:387-411)
+        top.vx = bx; top.vy = by;
+        top.inv1 = fdiv(fsub(bx, lx), fsub(by, ly));
+        top.inv2 = fdiv(fsub(bx, rx), fsub(by, ry));
+        top.y0 = f2i(fsub(ly, 0.5f)) + 1;                   // rows int(v0.y-.5) < row <= int(v2.y-.5)
+        top.y1 = f2i(fsub(by, 0.5f)) + 1;
+    }
+}
+
+// Pixel range [xl, xr) of one row of one half, X-clamped to the scissor (Rasterizer.h:376-378).
+SWR_HD void spanRow(const SpanHalf &h, int row, int scMinX, int scMaxX, int &xl, int &xr)
+{
+    xl = imax(scMinX, f2i(spanX(h.vx, h.vy, h.inv1, row)));
+    xr = imin(scMaxX, f2i(spanX(h.vx, h.vy, h.inv2, row)));
+}
+
+// Exact footprint of the two halves: the row-wise x is monotone in the row (every fp32 step of
+// spanX is monotone), so the extremes sit on the first / last row of each half.
+SWR_HD Box16 spanBox(const SpanHalf &bot, const SpanHalf &top, int scMinX, int scMaxX)
+{
+    int x0 = 32767, x1 = -32768, y0 = 32767, y1 = -32768;
+    const SpanHalf *hs[2] = { &bot, &top };
+    for (int k = 0; k < 2; ++k) {
+        const SpanHalf &h = *hs[k];
+        if (h.y0 >= h.y1) continue;
+        int xl, xr;
+        spanRow(h, h.y0, scMinX, scMaxX, xl, xr);
+        x0 = imin(x0, xl); x1 = imax(x1, xr - 1);
+        spanRow(h, h.y1 - 1, scMinX, scMaxX, xl, xr);
+        x0 = imin(x0, xl); x1 = imax(x1, xr - 1);
+        y0 = imin(y0, h.y0); y1 = imax(y1, h.y1 - 1);
+    }
+    return makeBox(x0, y0, x1, y1);
+}
+
+SWR_HD float4 mkf4(float a, float b, float c, float d) { float4 v; v.x = a; v.y = b; v.z = c; v.w = d; return v; }
+SWR_HD float u2f(uint32_t u)
+{
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(u);
+#else
+    union { uint32_t u; float f; } c; c.u = u; return c.f;
+#endif
+}
+SWR_HD uint32_t f2u(float f)
+{
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(f);
+#else
+    union { uint32_t u; float f; } c; c.f = f; return c.u;
+#endif
+}
+
+// Screen-space triangle -> record `rec`.  Cull / re-orient (VertexProcessor.cpp:319-345), setup
+// (TriangleEquations.h:47-71), footprint (Rasterizer.h:234-255 or the span halves).  Returns the
+// footprint box (dead when the triangle is dropped anywhere on the way).
+template <int NA, int NP>
+SWR_HD Box16 emitScreenTriangle(const GeomArgs &g, uint32_t rec, uint32_t ordinal, bool doCull,
+                                const CVert<NA, NP> &s0, const CVert<NA, NP> &s1, const CVert<NA, NP> &s2)
+{
+    const CVert<NA, NP> *v0 = &s0, *v1 = &s1, *v2 = &s2;
+    if (g.dbgVerts) {
+        float *d = g.dbgVerts + (size_t)rec * 12;
+        d[0] = s0.x; d[1] = s0.y; d[2] = s0.z; d[3] = s0.w;
+        d[4] = s1.x; d[5] = s1.y; d[6] = s1.z; d[7] = s1.w;
+        d[8] = s2.x; d[9] = s2.y; d[10] = s2.z; d[11] = s2.w;
+    }
+    if (doCull) {
+        const float facing = fsub(fmul(fsub(s0.x, s1.x), fsub(s2.y, s1.y)), fmul(fsub(s2.x, s1.x), fsub(s0.y, s1.y)));
+        if (facing < 0) {
+            if (g.cullMode == SWR_CULL_CW) return deadBox();
+        } else {
+            if (g.cullMode == SWR_CULL_CCW) return deadBox();
+            v0 = &s2; v2 = &s0;                             // std::swap(idx0, idx2)
+        }
+    }
+    EdgeEquation e0 = {}, e1 = {}, e2 = {};
+    e0.init(v1->x, v1->y, v2->x, v2->y);
+    e1.init(v2->x, v2->y, v0->x, v0->y);
+    e2.init(v0->x, v0->y, v1->x, v1->y);
+    const float area2 = fadd(fadd(e0.c, e1.c), e2.c);
+    if (area2 <= 0) return deadBox();                       // Rasterizer.h:231,315
+
+    // raster mode of this triangle (Rasterizer.h:413-445; Adaptive's literals are doubles)
+    bool span = g.rasterMode == SWR_RASTER_SPAN;
+    const float fminX = min3f(v0->x, v1->x, v2->x), fmaxX = max3f(v0->x, v1->x, v2->x);
+    const float fminY = min3f(v0->y, v1->y, v2->y), fmaxY = max3f(v0->y, v1->y, v2->y);
+    if (g.rasterMode == SWR_RASTER_ADAPTIVE) {
+        const float orient = fdiv(fsub(fmaxX, fminX), fsub(fmaxY, fminY));
+        span = !((double)orient > 0.4 && (double)orient < 1.6);
+    }
+
+    Box16 box;
+    if (span) {
+        SpanHalf bot, top;
+        spanSetup(v0->x, v0->y, v1->x, v1->y, v2->x, v2->y, bot, top);
+        box = spanBox(bot, top, g.scMinX, g.scMaxX);
+        if (box.x0 > box.x1) return box;
+        float4 *sp = g.span + (size_t)rec * 3;
+        sp[0] = mkf4(bot.vx, bot.vy, bot.inv1, bot.inv2);
+        sp[1] = mkf4(top.vx, top.vy, top.inv1, top.inv2);
+        sp[2] = mkf4(u2f((uint32_t)bot.y0), u2f((uint32_t)bot.y1), u2f((uint32_t)top.y0), u2f((uint32_t)top.y1));
+    } else {
+        int minX = f2i(fminX), maxX = f2i(fmaxX), minY = f2i(fminY), maxY = f2i(fmaxY);
+        minX = imax(minX, g.scMinX); maxX = imin(maxX, g.scMaxX);      // max stays the exclusive edge (P11)
+        minY = imax(minY, g.scMinY); maxY = imin(maxY, g.scMaxY);
+        minX &= ~7; maxX &= ~7; minY &= ~7; maxY &= ~7;
+        const int stepsX = (maxX - minX) / 8 + 1, stepsY = (maxY - minY) / 8 + 1;
+        if (stepsX <= 0 || stepsY <= 0) return deadBox();            // reference loop does not run (P23 aside)
+        box = makeBox(minX, minY, maxX + 7, maxY + 7);
+        if (box.x0 > box.x1) return box;
+    }
+
+    uint32_t flags = (e0.tie ? kTie0 : 0u) | (e1.tie ? kTie1 : 0u) | (e2.tie ? kTie2 : 0u) | (span ? kModeSpan : 0u);
+    float4 *hd = g.head + (size_t)rec * 3;
+    hd[0] = mkf4(e0.a, e0.b, e0.c, e1.a);
+    hd[1] = mkf4(e1.b, e1.c, e2.a, e2.b);
+    hd[2] = mkf4(e2.c, u2f(flags), u2f(ordinal), area2);
+
+    // interpolation planes (TriangleEquations.h:59-70), order: z?, invw?, avar[nA], pvar[nP]
+    float *pp = g.params + (size_t)rec * g.paramStride;
+    const float factor = fdiv(1.0f, area2);
+    ParameterEquation pe;
+    if (g.useZ) {
+        pe.init(v0->z, v1->z, v2->z, e0, e1, e2, factor);
+        pp[0] = pe.a; pp[1] = pe.b; pp[2] = pe.c; pp += 3;
+    }
+    float iw0 = 0.0f, iw1 = 0.0f, iw2 = 0.0f;
+    if (g.useW || g.nP > 0) {
+        iw0 = fdiv(1.0f, v0->w); iw1 = fdiv(1.0f, v1->w); iw2 = fdiv(1.0f, v2->w);
+        pe.init(iw0, iw1, iw2, e0, e1, e2, factor);
+        pp[0] = pe.a; pp[1] = pe.b; pp[2] = pe.c; pp += 3;
+    }
+#pragma unroll
+    for (int i = 0; i < NA; ++i) {
+        if (i < g.nA) {
+            pe.init(v0->a[i], v1->a[i], v2->a[i], e0, e1, e2, factor);
+            pp[0] = pe.a; pp[1] = pe.b; pp[2] = pe.c; pp += 3;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+        if (i < g.nP) {
+            pe.init(fmul(v0->p[i], iw0), fmul(v1->p[i], iw1), fmul(v2->p[i], iw2), e0, e1, e2, factor);
+            pp[0] = pe.a; pp[1] = pe.b; pp[2] = pe.c; pp += 3;
+        }
+    }
+    return box;
+}
+
+// Clip-space fan triangle -> screen -> record.
+template <int NA, int NP>
+SWR_HD Box16 emitClipTriangle(const GeomArgs &g, uint32_t rec, uint32_t ordinal,
+                              CVert<NA, NP> a, CVert<NA, NP> b, CVert<NA, NP> c)
+{
+    toScreen(g, a);
+    toScreen(g, b);
+    toScreen(g, c);
+    return emitScreenTriangle(g, rec, ordinal, true, a, b, c);
+}
+
+// Rasterizer.h:144-147
+SWR_HD bool scissorTest(int minX, int minY, int maxX, int maxY, float x, float y)
+{
+    return x >= i2f(minX) && x < i2f(maxX) && y >= i2f(minY) && y < i2f(maxY);
+}
+
+constexpr int kMaxLineSteps = 1 << 17;   // longer DDA walks cannot touch a <= 32767-pixel screen meaningfully
+
+// Screen-space line -> record (Rasterizer.h:175-222).  head0 = {x0, y0, stepx, stepy},
+// head1 = {steps, ordinal}; params = (start, step) pairs of z?, w?, avar[], pvar[].
+template <int NA, int NP>
+SWR_HD Box16 emitScreenLine(const GeomArgs &g, uint32_t rec, uint32_t ordinal, const CVert<NA, NP> &v0, const CVert<NA, NP> &v1)
+{
+    if (g.dbgVerts) {
+        float *d = g.dbgVerts + (size_t)rec * 12;
+        d[0] = v0.x; d[1] = v0.y; d[2] = v0.z; d[3] = v0.w;
+        d[4] = v1.x; d[5] = v1.y; d[6] = v1.z; d[7] = v1.w;
+        d[8] = d[9] = d[10] = d[11] = 0.0f;
+    }
+    const int ix0 = f2i(v0.x), iy0 = f2i(v0.y), ix1 = f2i(v1.x), iy1 = f2i(v1.y);
+    const int adx = ix1 > ix0 ? ix1 - ix0 : ix0 - ix1;
+    const int ady = iy1 > iy0 ? iy1 - iy0 : iy0 - iy1;
+    const int steps = imax(adx, ady);
+    if (steps <= 0) return deadBox();
+    if (steps > kMaxLineSteps) {
+#if defined(__CUDA_ARCH__)
+        atomicOr(g.errorFlag, 2u);
+        atomicOr(g.errorFlag + 1, 2u);      // sticky copy, reported by swr_finish
+#endif
+        return deadBox();
+    }
+    // fragments must pass the float scissor test, so the footprint is inside the scissor;
+    // +-2 pixels absorb the drift of the repeated additions
+    Box16 box = makeBox(imax(imin(ix0, ix1) - 2, g.scMinX), imax(imin(iy0, iy1) - 2, g.scMinY),
+                        imin(imax(ix0, ix1) + 2, g.scMaxX - 1), imin(imax(iy0, iy1) + 2, g.scMaxY - 1));
+    if (box.x0 > box.x1) return box;
+    const float fs = i2f(steps);
+    float4 *hd = g.head + (size_t)rec * 3;
+    hd[0] = mkf4(v0.x, v0.y, fdiv(fsub(v1.x, v0.x), fs), fdiv(fsub(v1.y, v0.y), fs));
+    hd[1] = mkf4(u2f((uint32_t)steps), u2f(ordinal), 0.0f, 0.0f);
+    float *pp = g.params + (size_t)rec * g.paramStride;
+    if (g.useZ) { pp[0] = v0.z; pp[1] = fdiv(fsub(v1.z, v0.z), fs); pp += 2; }
+    if (g.useW) { pp[0] = v0.w; pp[1] = fdiv(fsub(v1.w, v0.w), fs); pp += 2; }
+#pragma unroll
+    for (int i = 0; i < NA; ++i)
+        if (i < g.nA) { pp[0] = v0.a[i]; pp[1] = fdiv(fsub(v1.a[i], v0.a[i]), fs); pp += 2; }
+#pragma unroll
+    for (int i = 0; i < NP; ++i)
+        if (i < g.nP) { pp[0] = v0.p[i]; pp[1] = fdiv(fsub(v1.p[i], v0.p[i]), fs); pp += 2; }
+    return box;
+}
+
+// Screen-space point -> record (Rasterizer.h:149-173).
+template <int NA, int NP>
+SWR_HD Box16 emitScreenPoint(const GeomArgs &g, uint32_t rec, uint32_t ordinal, const CVert<NA, NP> &v)
+{
+    if (g.dbgVerts) {
+        float *d = g.dbgVerts + (size_t)rec * 12;
+        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+        for (int i = 4; i < 12; ++i) d[i] = 0.0f;
+    }
+    if (!scissorTest(g.scMinX, g.scMinY, g.scMaxX, g.scMaxY, v.x, v.y)) return deadBox();
+    const int ix = f2i(v.x), iy = f2i(v.y);
+    Box16 box = makeBox(ix, iy, ix, iy);
+    if (box.x0 > box.x1) return box;
+    float4 *hd = g.head + (size_t)rec * 3;
+    hd[0] = mkf4(v.x, v.y, 0.0f, 0.0f);
+    hd[1] = mkf4(0.0f, u2f(ordinal), 0.0f, 0.0f);
+    float *pp = g.params + (size_t)rec * g.paramStride;
+    if (g.useZ) { pp[0] = v.z; pp += 1; }
+    if (g.useW) { pp[0] = v.w; pp += 1; }
+#pragma unroll
+    for (int i = 0; i < NA; ++i)
+        if (i < g.nA) { pp[0] = v.a[i]; pp += 1; }
+#pragma unroll
+    for (int i = 0; i < NP; ++i)
+        if (i < g.nP) { pp[0] = v.p[i]; pp += 1; }
+    return box;
+}
+
+// One input line: VertexProcessor.cpp:167-215 + LineClipper.cpp:30-56.
+template <int NA, int NP>
+SWR_HD Box16 emitClipLine(const GeomArgs &g, uint32_t rec, uint32_t ordinal, const CVert<NA, NP> &c0, const CVert<NA, NP> &c1)
+{
+    const int m0 = outcode(c0.x, c0.y, c0.z, c0.w), m1 = outcode(c1.x, c1.y, c1.z, c1.w);
+    const int mask = m0 | m1;
+    float t0 = 0.0f, t1 = 1.0f;
+    for (int pl = 0; pl < 6; ++pl) {
+        if (!(mask & (1 << pl))) continue;
+        const float d0 = planeDist(pl, c0.x, c0.y, c0.z, c0.w);
+        const float d1 = planeDist(pl, c1.x, c1.y, c1.z, c1.w);
+        const bool n0 = d0 < 0, n1 = d1 < 0;
+        if (n0 && n1) return deadBox();
+        if (n0) {
+            const float t = fdiv(-d0, fsub(d1, d0));
+            t0 = t0 < t ? t : t0;                           // std::max(t0, t)
+        } else {
+            const float t = fdiv(d0, fsub(d0, d1));
+            t1 = t < t1 ? t : t1;                           // std::min(t1, t)
+        }
+    }
+    CVert<NA, NP> a = c0, b = c1;
+    if (m0) lerpVert(a, c0, c1, t0);
+    if (m1) lerpVert(b, c0, c1, t1);
+    toScreen(g, a);
+    toScreen(g, b);
+    return emitScreenLine(g, rec, ordinal, a, b);
+}
+
+#if defined(__CUDACC__)
+
+template <class VS>
+SWR_D void shadeVertex(const GeomArgs &g, int index, CVert<VS::AVarCount, VS::PVarCount> &o)
+{
+    VertexShaderInput in;
+#pragma unroll
+    for (int i = 0; i < MaxVertexAttribs; ++i)
+        in[i] = (i < VS::AttribCount) ? (const void *)((const char *)g.attribPtr[i] + (size_t)g.attribStride[i] * (size_t)index)
+                                      : nullptr;                     // VertexProcessor.cpp:134-150
+    VertexShaderOutput out;
+    VS::processVertex(in, &out);
+    o.x = out.x; o.y = out.y; o.z = out.z; o.w = out.w;
+#pragma unroll
+    for (int i = 0; i < VS::AVarCount; ++i) o.a[i] = out.avar[i];
+#pragma unroll
+    for (int i = 0; i < VS::PVarCount; ++i) o.p[i] = out.pvar[i];
+}
+
+// Union of the warp's boxes -> gbox[group]; mark every screen tile the union touches in the
+// tile x chunk bitmap.
+SWR_D void publishGroup(const GeomArgs &g, Box16 box, uint32_t group, uint32_t chunk)
+{
+    int x0 = box.x0, y0 = box.y0, x1 = box.x1, y1 = box.y1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        x0 = min(x0, __shfl_xor_sync(0xffffffffu, x0, o));
+        y0 = min(y0, __shfl_xor_sync(0xffffffffu, y0, o));
+        x1 = max(x1, __shfl_xor_sync(0xffffffffu, x1, o));
+        y1 = max(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+    }
+    const int lane = threadIdx.x & 31;
+    if (lane == 0) {
+        Box16 u; u.x0 = (int16_t)x0; u.y0 = (int16_t)y0; u.x1 = (int16_t)x1; u.y1 = (int16_t)y1;
+        g.gbox[group] = u;
+    }
+    if (x0 > x1) return;
+    const int tx0 = x0 >> g.tileShift, ty0 = y0 >> g.tileShift;
+    const int tx1 = min(x1 >> g.tileShift, g.tilesX - 1), ty1 = min(y1 >> g.tileShift, g.tilesY - 1);
+    if (tx0 > tx1 || ty0 > ty1) return;
+    const int nx = tx1 - tx0 + 1, nt = nx * (ty1 - ty0 + 1);
+    const uint32_t bit = 1u << (chunk & 31);
+    for (int i = lane; i < nt; i += 32) {
+        const int tile = (ty0 + i / nx) * g.tilesX + tx0 + i % nx;
+        uint32_t *wp = g.tilemap + (size_t)tile * g.chunkWords + (chunk >> 5);
+        if (!(*(volatile uint32_t *)wp & bit)) atomicOr(wp, bit);
+    }
+}
+
+template <class VS>
+__global__ void __launch_bounds__(kGeomThreads) geometryKernel(const GeomArgs g)
+{
+    constexpr int NA = VS::AVarCount, NP = VS::PVarCount;
+    typedef CVert<NA, NP> V;
+    constexpr int kMaxExtraGroups = kBatch * (kMaxFan - 1) / kGroup;
+
+    __shared__ uint16_t sExtraCnt[kBatch];     // fan extras per primitive of this batch
+    __shared__ uint16_t sExtraOfs[kBatch];     // exclusive prefix in primitive order
+    __shared__ uint32_t sWarpSum[kGeomThreads / 32];
+    __shared__ uint32_t sExtraBase, sExtraTotal;
+    __shared__ int sGx0[kMaxExtraGroups], sGy0[kMaxExtraGroups], sGx1[kMaxExtraGroups], sGy1[kMaxExtraGroups];
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int batch = blockIdx.x;
+    const int primBase = batch * kBatch;
+    const int cnt = min(kBatch, g.numPrims - primBase);
+    const uint32_t ord0 = (g.firstBatch + (uint32_t)batch) * SWR_ORDINAL_STRIDE;
+    const int per = g.drawMode + 1;
+    bool anyExtra = false;
+
+    for (int r = 0; r < kBatch / kGeomThreads; ++r) {
+        const int slot = r * kGeomThreads + tid;
+        const uint32_t rec = (uint32_t)(primBase + slot);
+        Box16 box = deadBox();
+        int extras = 0;
+        if (slot < cnt) {
+            const int32_t *ip = g.indices + (size_t)rec * per;
+            const uint32_t ordinal = ord0 + (uint32_t)slot;
+            if (g.drawMode == SWR_DRAW_TRIANGLE) {
+                V v0, v1, v2;
+                shadeVertex<VS>(g, ip[0], v0);
+                shadeVertex<VS>(g, ip[1], v1);
+                shadeVertex<VS>(g, ip[2], v2);
+                const int mask = outcode(v0.x, v0.y, v0.z, v0.w) | outcode(v1.x, v1.y, v1.z, v1.w) |
+                                 outcode(v2.x, v2.y, v2.z, v2.w);
+                if (mask == 0) {
+                    box = emitClipTriangle<NA, NP>(g, rec, ordinal, v0, v1, v2);
+                } else {
+                    V a[kMaxPoly], b[kMaxPoly], *poly;      // rare path: polygons live in local memory
+                    a[0] = v0; a[1] = v1; a[2] = v2;
+                    const int n = clipTriangle<NA, NP>(a, b, mask, &poly);
+                    if (n >= 3) {
+                        box = emitClipTriangle<NA, NP>(g, rec, ordinal, poly[0], poly[1], poly[2]);
+                        extras = n - 3;
+                    }
+                }
+            } else if (g.drawMode == SWR_DRAW_LINE) {
+                V c0, c1;
+                shadeVertex<VS>(g, ip[0], c0);
+                shadeVertex<VS>(g, ip[1], c1);
+                box = emitClipLine<NA, NP>(g, rec, ordinal, c0, c1);
+            } else {
+                V c0;
+                shadeVertex<VS>(g, ip[0], c0);
+                if (outcode(c0.x, c0.y, c0.z, c0.w) == 0) {     // VertexProcessor.cpp:152-165
+                    toScreen(g, c0);
+                    box = emitScreenPoint<NA, NP>(g, rec, ordinal, c0);
+                }
+            }
+        }
+        g.bbox[rec] = box;
+        sExtraCnt[slot] = (uint16_t)extras;
+        anyExtra |= extras > 0;
+        publishGroup(g, box, rec >> 5, 2u * (uint32_t)batch);
+    }
+
+    // ---- clipper fan extras: appended behind the batch's original slots, in primitive order
+    if (!__syncthreads_or(anyExtra)) {
+        if (tid == 0) g.extra[batch] = make_uint2(0u, 0u);
+        return;
+    }
+    {   // exclusive scan of sExtraCnt over the 1024 slots: thread t owns slots 4t..4t+3
+        uint32_t c0 = sExtraCnt[4 * tid], c1 = sExtraCnt[4 * tid + 1], c2 = sExtraCnt[4 * tid + 2], c3 = sExtraCnt[4 * tid + 3];
+        uint32_t sum = c0 + c1 + c2 + c3, incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += n;
+        }
+        if (lane == 31) sWarpSum[wid] = incl;
+        __syncthreads();
+        uint32_t base = 0;
+        for (int w = 0; w < wid; ++w) base += sWarpSum[w];
+        uint32_t ex = base + incl - sum;
+        sExtraOfs[4 * tid] = (uint16_t)ex;
+        sExtraOfs[4 * tid + 1] = (uint16_t)(ex + c0);
+        sExtraOfs[4 * tid + 2] = (uint16_t)(ex + c0 + c1);
+        sExtraOfs[4 * tid + 3] = (uint16_t)(ex + c0 + c1 + c2);
+        if (tid == kGeomThreads - 1) {
+            const uint32_t total = ex + sum;
+            const uint32_t padded = (total + kGroup - 1) & ~(uint32_t)(kGroup - 1);
+            uint32_t b0 = atomicAdd(g.extraAlloc, padded);
+            if (b0 + padded > g.extrasEnd) { atomicOr(g.errorFlag, 1u); atomicOr(g.errorFlag + 1, 1u); b0 = 0xffffffffu; }
+            sExtraBase = b0;
+            sExtraTotal = total;
+            g.extra[batch] = (b0 == 0xffffffffu) ? make_uint2(0u, 0u) : make_uint2(b0, total);
+        }
+        for (int i = tid; i < kMaxExtraGroups; i += kGeomThreads) { sGx0[i] = 32767; sGy0[i] = 32767; sGx1[i] = -32768; sGy1[i] = -32768; }
+        __syncthreads();
+    }
+    const uint32_t ebase = sExtraBase, etotal = sExtraTotal;
+    if (ebase == 0xffffffffu) return;                       // scratch exhausted: flagged, draw is void
+
+    for (int r = 0; r < kBatch / kGeomThreads; ++r) {
+        const int slot = r * kGeomThreads + tid;
+        const int extras = sExtraCnt[slot];
+        if (extras == 0) continue;
+        const uint32_t ofs = sExtraOfs[slot];
+        const int32_t *ip = g.indices + (size_t)(primBase + slot) * 3;
+        V a[kMaxPoly], b[kMaxPoly], *poly;
+        shadeVertex<VS>(g, ip[0], a[0]);
+        shadeVertex<VS>(g, ip[1], a[1]);
+        shadeVertex<VS>(g, ip[2], a[2]);
+        const int mask = outcode(a[0].x, a[0].y, a[0].z, a[0].w) | outcode(a[1].x, a[1].y, a[1].z, a[1].w) |
+                         outcode(a[2].x, a[2].y, a[2].z, a[2].w);
+        const int n = clipTriangle<NA, NP>(a, b, mask, &poly);
+        for (int k = 1; k + 2 < n; ++k) {                   // fan (p0, p[k+1], p[k+2]), VertexProcessor.cpp:257-261
+            const uint32_t e = ofs + (uint32_t)(k - 1);
+            const uint32_t rec = ebase + e;
+            const Box16 box = emitClipTriangle<NA, NP>(g, rec, ord0 + (uint32_t)cnt + e, poly[0], poly[k + 1], poly[k + 2]);
+            g.bbox[rec] = box;
+            if (box.x0 <= box.x1) {
+                atomicMin(&sGx0[e >> 5], (int)box.x0); atomicMin(&sGy0[e >> 5], (int)box.y0);
+                atomicMax(&sGx1[e >> 5], (int)box.x1); atomicMax(&sGy1[e >> 5], (int)box.y1);
+            }
+        }
+    }
+    __syncthreads();
+    const uint32_t padded = (etotal + kGroup - 1) & ~(uint32_t)(kGroup - 1);
+    for (uint32_t e = etotal + tid; e < padded; e += kGeomThreads) g.bbox[ebase + e] = deadBox();
+    const int ngroups = (int)(padded >> 5);
+    for (int gi = wid; gi < ngroups; gi += kGeomThreads / 32) {
+        Box16 u; u.x0 = (int16_t)sGx0[gi]; u.y0 = (int16_t)sGy0[gi]; u.x1 = (int16_t)sGx1[gi]; u.y1 = (int16_t)sGy1[gi];
+        publishGroup(g, u, (ebase >> 5) + (uint32_t)gi, 2u * (uint32_t)batch + 1u);
+    }
+}
+
+template <class VS>
+void launchGeometry(const void *args, void *stream)
+{
+    const GeomArgs *g = static_cast<const GeomArgs *>(args);
+    const int batches = (g->numPrims + kBatch - 1) / kBatch;
+    if (batches > 0) geometryKernel<VS><<<batches, kGeomThreads, 0, (cudaStream_t)stream>>>(*g);
+}
+
+template <class VS>
+const swr_vertex_shader *vertexShaderBinding(const char *name = "user")
+{
+    static const swr_vertex_shader d = { &launchGeometry<VS>, &uploadUniforms, VS::AttribCount, VS::AVarCount, VS::PVarCount, name };
+    return &d;
+}
+
+#endif // __CUDACC__
+
+} // namespace detail
+} // namespace swr

@@ -1,0 +1,717 @@
+// swr/detail/tile.cuh -- the tile kernel (K4+K5+K6 of SURVEY.md 2.3): order-preserving binning,
+// coverage and shading of one screen tile per CTA, templated on the user's pixel shader so
+// drawPixel is inlined.
+//
+// Per tile (T x T pixels, T = 32 or 64, so every reference 8x8 block lies in exactly one tile):
+//   F1  read the tile's row of the tile x chunk bitmap      -> chunks that may touch the tile,
+//   F2  test their 32-record group boxes                     -> groups,
+//   F3  test the groups' record boxes                        -> queue of primitives,
+//       each step is a block-wide ordered compaction (ballot-free prefix sums), so the queue is in
+//       ascending (chunk, record) order = the reference's emission order, with no atomics and no sort;
+//   A   one thread per (primitive, 8x8 block) item: exact coverage as a 64-bit mask
+//       Block:  Rasterizer.h:257-305 corner classification (incl. the "special case" skip) and
+//               the per-pixel add chains of PixelShaderBase.h:55-94 / EdgeData.h:45-66
+//       Span:   per-row [xl, xr) of Rasterizer.h:360-411 (no edge tests)
+//       lines:  the DDA walk of Rasterizer.h:175-207; points: Rasterizer.h:149-158
+//   B   each 8x8 block is owned by one warp for the whole tile; it walks the block's items in
+//       queue order, 32 fragments at a time (one lane per fragment); fragments of different
+//       primitives that hit the same pixel are serialised in emission order.  Every lane
+//       replays the reference's incremental fp32 chain for its own pixel (PixelData.h:61-125),
+//       so z / w / varyings are bit-identical, then calls PixelShader::drawPixel.
+// Registered render targets are staged in shared memory (block-linear) for the whole tile and
+// moved with 128-bit loads / stores.
+#pragma once
+
+#include "common.h"
+#include "geometry.cuh"
+#include "../PixelShaderBase.h"
+#include "../Uniforms.h"
+
+#if defined(__CUDACC__)
+
+namespace swr {
+namespace detail {
+
+constexpr int kQueue = 512;          // primitives per flush
+constexpr int kItems = 2048;         // (primitive, block) items per flush
+constexpr int kChunkList = 1024;
+constexpr int kGroupList = 1024;
+constexpr int kTileWarps = kTileThreads / 32;
+
+template <int TLOG, int NRT>
+struct TileSmem {
+    static constexpr int T = 1 << TLOG;
+    static constexpr int BPR = T / 8;                 // blocks per tile row
+    static constexpr int NB = BPR * BPR;              // blocks per tile
+    static constexpr int QW = kQueue / 32;            // bitmap words per block
+    static constexpr size_t rtBytes = (size_t)NRT * T * T * 4;
+    static constexpr size_t offMasks = (rtBytes + 15) & ~(size_t)15;
+    static constexpr size_t offBlockmap = offMasks + (size_t)kItems * 8;
+    static constexpr size_t offQRec = offBlockmap + (size_t)NB * QW * 4;
+    static constexpr size_t offQRange = offQRec + (size_t)kQueue * 4;
+    static constexpr size_t offQItem = offQRange + (size_t)kQueue * 4;
+    static constexpr size_t offChunkGroup = offQItem + (size_t)(kQueue + 1) * 4 + 12;
+    static constexpr size_t offChunkPair = offChunkGroup + (size_t)kChunkList * 4;
+    static constexpr size_t offGroupList = offChunkPair + (size_t)(kChunkList + 1) * 4 + 12;
+    static constexpr size_t offScan = offGroupList + (size_t)kGroupList * 4;
+    static constexpr size_t offCtl = offScan + 2 * (kTileWarps + 1) * 8;
+    static constexpr size_t bytes = offCtl + 64;
+};
+
+struct Ctl { uint32_t accQ, accItems; };
+
+// Exclusive block scan of a packed (hi: count, lo: sum) pair.  Two barriers; scratch is double
+// buffered so back-to-back calls need no trailing barrier.
+SWR_D uint64_t blockScan(uint64_t v, uint64_t &total, uint64_t *scratch, int &phase)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint64_t *s = scratch + phase * (kTileWarps + 1);
+    phase ^= 1;
+    uint64_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint64_t n = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += n;
+    }
+    if (lane == 31) s[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        uint64_t w = lane < kTileWarps ? s[lane] : 0;
+        uint64_t wi = w;
+#pragma unroll
+        for (int o = 1; o < kTileWarps; o <<= 1) {
+            uint64_t n = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += n;
+        }
+        if (lane < kTileWarps) s[lane] = wi - w;
+        if (lane == kTileWarps - 1) s[kTileWarps] = wi;
+    }
+    __syncthreads();
+    total = s[kTileWarps];
+    return incl - v + s[wid];
+}
+
+SWR_D bool boxOverlaps(const Box16 b, int X0, int Y0, int X1, int Y1)
+{
+    return b.x0 <= b.x1 && b.x0 <= X1 && b.x1 >= X0 && b.y0 <= Y1 && b.y1 >= Y0;
+}
+
+// position of the n-th (0-based) set bit of a 64-bit mask
+SWR_D int nthSetBit64(uint64_t m, int n)
+{
+    const uint32_t lo = (uint32_t)m, hi = (uint32_t)(m >> 32);
+    const int cl = __popc(lo);
+    return n < cl ? (int)__fns(lo, 0, n + 1) : 32 + (int)__fns(hi, 0, n - cl + 1);
+}
+
+SWR_HD bool edgeIn(float v, bool tie) { return v > 0 || (v == 0 && tie); }   // EdgeEquation.h:58-61
+
+// ---- coverage of one 8x8 block ------------------------------------------------------------------
+// Block mode: Rasterizer.h:257-305 + PixelShaderBase.h:55-94.  (gx, gy) = block origin.
+SWR_HD uint64_t coverBlock(const float4 h0, const float4 h1, const float4 h2, int gx, int gy)
+{
+    const float ea[3] = { h0.x, h0.w, h1.z }, eb[3] = { h0.y, h1.x, h1.w }, ec[3] = { h0.z, h1.y, h2.x };
+    const uint32_t flags = f2u(h2.y);
+    const bool tie[3] = { (flags & kTie0) != 0, (flags & kTie1) != 0, (flags & kTie2) != 0 };
+    const float xf = fadd(i2f(gx), 0.5f), yf = fadd(i2f(gy), 0.5f);
+    const float s = 7.0f;
+    float e00[3];
+    bool in[4][3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        e00[k] = fadd(fadd(fmul(ea[k], xf), fmul(eb[k], yf)), ec[k]);      // EdgeData.h:37-42
+        const float e01 = fadd(e00[k], fmul(eb[k], s));                    // stepY(s)
+        const float e10 = fadd(e00[k], fmul(ea[k], s));                    // stepX(s)
+        const float e11 = fadd(e01, fmul(ea[k], s));
+        in[0][k] = edgeIn(e00[k], tie[k]); in[1][k] = edgeIn(e01, tie[k]);
+        in[2][k] = edgeIn(e10, tie[k]); in[3][k] = edgeIn(e11, tie[k]);
+    }
+    int all = 0;
+    bool same = true;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        all += (in[j][0] && in[j][1] && in[j][2]) ? 1 : 0;
+        same = same && ((in[j][0] == in[j][1]) == in[j][2]);               // C++ chained '==' (Rasterizer.h:287-290)
+    }
+    if (all == 4) return ~0ull;                                            // drawBlock<false>
+    if (all == 0 && same) return 0ull;                                     // "special case": block skipped
+    uint64_t mask = 0;
+    float r0 = e00[0], r1 = e00[1], r2 = e00[2];
+#pragma unroll
+    for (int yy = 0; yy < 8; ++yy) {
+        float v0 = r0, v1 = r1, v2 = r2;
+#pragma unroll
+        for (int xx = 0; xx < 8; ++xx) {
+            if (edgeIn(v0, tie[0]) && edgeIn(v1, tie[1]) && edgeIn(v2, tie[2])) mask |= 1ull << (yy * 8 + xx);
+            v0 = fadd(v0, ea[0]); v1 = fadd(v1, ea[1]); v2 = fadd(v2, ea[2]);
+        }
+        r0 = fadd(r0, eb[0]); r1 = fadd(r1, eb[1]); r2 = fadd(r2, eb[2]);
+    }
+    return mask;
+}
+
+SWR_HD SpanHalf loadHalf(const float4 v, uint32_t y0, uint32_t y1)
+{
+    SpanHalf h; h.vx = v.x; h.vy = v.y; h.inv1 = v.z; h.inv2 = v.w; h.y0 = (int)y0; h.y1 = (int)y1;
+    return h;
+}
+
+// Span mode: rows of the two halves, [xl, xr) per row (Rasterizer.h:360-411).
+SWR_HD uint64_t coverSpan(const float4 s0, const float4 s1, const float4 s2, int gx, int gy, int scMinX, int scMaxX)
+{
+    const SpanHalf bot = loadHalf(s0, f2u(s2.x), f2u(s2.y)), top = loadHalf(s1, f2u(s2.z), f2u(s2.w));
+    uint64_t mask = 0;
+#pragma unroll
+    for (int yy = 0; yy < 8; ++yy) {
+        const int row = gy + yy;
+        const bool inBot = row >= bot.y0 && row < bot.y1, inTop = row >= top.y0 && row < top.y1;
+        if (!inBot && !inTop) continue;
+        int xl, xr;
+        spanRow(inBot ? bot : top, row, scMinX, scMaxX, xl, xr);
+        const int a = imax(xl - gx, 0), b = imin(xr - gx, 8);
+        if (a < b) mask |= (uint64_t)((0xffu >> (8 - (b - a))) << a) << (yy * 8);
+    }
+    return mask;
+}
+
+// Lines: pixels of the DDA walk that fall into this block and pass the float scissor test.
+SWR_HD uint64_t coverLine(const float4 h0, const float4 h1, int gx, int gy, const TileArgs &t)
+{
+    float x = h0.x, y = h0.y;
+    const int steps = (int)f2u(h1.x);
+    uint64_t mask = 0;
+    for (int k = 0; k < steps; ++k) {
+        if (scissorTest(t.scMinX, t.scMinY, t.scMaxX, t.scMaxY, x, y)) {
+            const int lx = f2i(x) - gx, ly = f2i(y) - gy;
+            if ((unsigned)lx < 8u && (unsigned)ly < 8u) mask |= 1ull << (ly * 8 + lx);
+        }
+        x = fadd(x, h0.z);
+        y = fadd(y, h0.w);
+    }
+    return mask;
+}
+
+// ---- shading --------------------------------------------------------------------------------------
+template <class PS>
+struct PsTraits {
+    static constexpr int NA = PS::AVarCount, NP = PS::PVarCount;
+    static constexpr bool Z = PS::InterpolateZ != 0, W = PS::InterpolateW != 0;
+    static constexpr bool WP = W || NP > 0;               // PixelData.h:67,89,107
+    static constexpr int NRT = PS::RenderTargets;
+};
+
+// One fragment of a triangle.  Block mode: start at the block origin, `yy` row steps, then `xx`
+// column steps (PixelShaderBase.h:61-92).  Span mode: start at (xl + .5, y + .5), x - xl column
+// steps (PixelShaderBase.h:96-112).  All lanes run the same instruction stream (the 7+7 / span
+// steps are predicated adds), so there is no divergence between fragments of a round.
+#pragma nv_exec_check_disable
+template <class PS>
+SWR_HD void shadeTriangleFragment(const TileArgs &t, uint32_t rec, int gx, int gy, int xx, int yy, PixelData &p)
+{
+    typedef PsTraits<PS> TR;
+    const float4 h2 = t.head[(size_t)rec * 3 + 2];
+    const uint32_t flags = f2u(h2.y);
+    const float *pl = t.params + (size_t)rec * t.paramStride;
+    p.primitiveOrdinal = f2u(h2.z);
+    p.x = gx + xx;
+    p.y = gy + yy;
+
+    float xf, yf;
+    int nrow, ncol;
+    if (flags & kModeSpan) {
+        const float4 *sp = t.span + (size_t)rec * 3;
+        const float4 s2 = sp[2];
+        const SpanHalf bot = loadHalf(sp[0], f2u(s2.x), f2u(s2.y)), top = loadHalf(sp[1], f2u(s2.z), f2u(s2.w));
+        const bool inBot = p.y >= bot.y0 && p.y < bot.y1;
+        const int xl = imax(t.scMinX, f2i(spanX(inBot ? bot.vx : top.vx, inBot ? bot.vy : top.vy, inBot ? bot.inv1 : top.inv1, p.y)));
+        xf = fadd(i2f(xl), 0.5f);
+        yf = fadd(i2f(p.y), 0.5f);
+        nrow = 0;
+        ncol = p.x - xl;
+    } else {
+        xf = fadd(i2f(gx), 0.5f);
+        yf = fadd(i2f(gy), 0.5f);
+        nrow = yy;
+        ncol = xx;
+    }
+
+    TriangleEquations eq;
+    {
+        const float4 h0 = t.head[(size_t)rec * 3], h1 = t.head[(size_t)rec * 3 + 1];
+        eq.area2 = h2.w;
+        eq.e0.a = h0.x; eq.e0.b = h0.y; eq.e0.c = h0.z; eq.e0.tie = (flags & kTie0) != 0;
+        eq.e1.a = h0.w; eq.e1.b = h1.x; eq.e1.c = h1.y; eq.e1.tie = (flags & kTie1) != 0;
+        eq.e2.a = h1.z; eq.e2.b = h1.w; eq.e2.c = h2.x; eq.e2.tie = (flags & kTie2) != 0;
+    }
+
+    auto chain = [&](const float a, const float b, const float c) -> float {
+        float v = fadd(fadd(fmul(a, xf), fmul(b, yf)), c);          // ParameterEquation::evaluate
+        if (flags & kModeSpan) {
+            for (int s = 0; s < ncol; ++s) v = fadd(v, a);
+        } else {
+#pragma unroll
+            for (int s = 0; s < 7; ++s) if (s < nrow) v = fadd(v, b);   // stepY
+#pragma unroll
+            for (int s = 0; s < 7; ++s) if (s < ncol) v = fadd(v, a);   // stepX
+        }
+        return v;
+    };
+
+    int o = 0;
+    if (TR::Z) {
+        eq.z.a = pl[0]; eq.z.b = pl[1]; eq.z.c = pl[2];
+        p.z = chain(eq.z.a, eq.z.b, eq.z.c);
+        o += 3;
+    }
+    if (TR::WP) {
+        eq.invw.a = pl[o]; eq.invw.b = pl[o + 1]; eq.invw.c = pl[o + 2];
+        p.invw = chain(eq.invw.a, eq.invw.b, eq.invw.c);
+        p.w = fdiv(1.0f, p.invw);
+        o += 3;
+    }
+    eq.avar.planes = pl + o;
+#pragma unroll
+    for (int i = 0; i < TR::NA; ++i) p.avar[i] = chain(pl[o + 3 * i], pl[o + 3 * i + 1], pl[o + 3 * i + 2]);
+    o += 3 * TR::NA;
+    eq.pvar.planes = pl + o;
+#pragma unroll
+    for (int i = 0; i < TR::NP; ++i) {
+        p.pvarTemp[i] = chain(pl[o + 3 * i], pl[o + 3 * i + 1], pl[o + 3 * i + 2]);
+        p.pvar[i] = fmul(p.pvarTemp[i], p.w);
+    }
+    p.equations = &eq;
+    PS::drawPixel(p);
+}
+
+// All hits of pixel (px, py) by one line, in step order (Rasterizer.h:175-207, 160-173).
+#pragma nv_exec_check_disable
+template <class PS>
+SWR_HD int shadeLineFragments(const TileArgs &t, uint32_t rec, int px, int py, PixelData &p)
+{
+    typedef PsTraits<PS> TR;
+    const float4 h0 = t.head[(size_t)rec * 3], h1 = t.head[(size_t)rec * 3 + 1];
+    const float *pl = t.params + (size_t)rec * t.paramStride;
+    const int steps = (int)f2u(h1.x);
+    p.primitiveOrdinal = f2u(h1.y);
+    p.equations = nullptr;
+    float x = h0.x, y = h0.y;
+    int o = 0;
+    float z = 0.0f, dz = 0.0f, w = 0.0f, dw = 0.0f;
+    float av[TR::NA > 0 ? TR::NA : 1], da[TR::NA > 0 ? TR::NA : 1], pv[TR::NP > 0 ? TR::NP : 1], dp[TR::NP > 0 ? TR::NP : 1];
+    if (TR::Z) { z = pl[o]; dz = pl[o + 1]; o += 2; }
+    if (TR::W) { w = pl[o]; dw = pl[o + 1]; o += 2; }
+#pragma unroll
+    for (int i = 0; i < TR::NA; ++i) { av[i] = pl[o]; da[i] = pl[o + 1]; o += 2; }
+#pragma unroll
+    for (int i = 0; i < TR::NP; ++i) { pv[i] = pl[o]; dp[i] = pl[o + 1]; o += 2; }
+    int drawn = 0;
+    for (int k = 0; k < steps; ++k) {
+        if (f2i(x) == px && f2i(y) == py && scissorTest(t.scMinX, t.scMinY, t.scMaxX, t.scMaxY, x, y)) {
+            p.x = px;
+            p.y = py;
+            if (TR::Z) p.z = z;
+            if (TR::W) { p.w = w; p.invw = fdiv(1.0f, w); }
+#pragma unroll
+            for (int i = 0; i < TR::NA; ++i) p.avar[i] = av[i];
+#pragma unroll
+            for (int i = 0; i < TR::NP; ++i) p.pvar[i] = pv[i];
+            PS::drawPixel(p);
+            ++drawn;
+        }
+        x = fadd(x, h0.z);
+        y = fadd(y, h0.w);
+        if (TR::Z) z = fadd(z, dz);
+        if (TR::W) w = fadd(w, dw);
+#pragma unroll
+        for (int i = 0; i < TR::NA; ++i) av[i] = fadd(av[i], da[i]);
+#pragma unroll
+        for (int i = 0; i < TR::NP; ++i) pv[i] = fadd(pv[i], dp[i]);
+    }
+    return drawn;
+}
+
+#pragma nv_exec_check_disable
+template <class PS>
+SWR_HD void shadePointFragment(const TileArgs &t, uint32_t rec, int px, int py, PixelData &p)
+{
+    typedef PsTraits<PS> TR;
+    const float4 h1 = t.head[(size_t)rec * 3 + 1];
+    const float *pl = t.params + (size_t)rec * t.paramStride;
+    p.primitiveOrdinal = f2u(h1.y);
+    p.equations = nullptr;
+    p.x = px;
+    p.y = py;
+    int o = 0;
+    if (TR::Z) { p.z = pl[o]; o += 1; }
+    if (TR::W) { p.w = pl[o]; p.invw = fdiv(1.0f, p.w); o += 1; }
+#pragma unroll
+    for (int i = 0; i < TR::NA; ++i) p.avar[i] = pl[o + i];
+    o += TR::NA;
+#pragma unroll
+    for (int i = 0; i < TR::NP; ++i) p.pvar[i] = pl[o + i];
+    PS::drawPixel(p);
+}
+
+// ---- staged render targets ------------------------------------------------------------------------
+// Shared-memory layout is block-linear: pixel (lx, ly) of the tile lives at word
+// ((ly/8)*BPR + lx/8)*64 + (ly%8)*8 + lx%8, so one 8x8 block is 256 contiguous bytes and a full
+// block round of 32 lanes touches 32 distinct banks.
+template <int TLOG, int NRT, bool STORE>
+SWR_D void moveTile(const TileArgs &t, char *rtSmem, int X0, int Y0)
+{
+    constexpr int T = 1 << TLOG, BPR = T / 8;
+#pragma unroll 1
+    for (int s = 0; s < NRT; ++s) {
+        char *g = (char *)t.rt[s].ptr;
+        const int pitch = t.rt[s].pitch;
+        uint32_t *sm = (uint32_t *)(rtSmem + (size_t)s * T * T * 4);
+        const bool vec = ((((uintptr_t)g) | (uintptr_t)pitch) & 15) == 0 && (t.rtWidth & 3) == 0;
+        if (vec) {
+            for (int i = threadIdx.x; i < T * T / 4; i += kTileThreads) {
+                const int ly = i / (T / 4), lx = (i % (T / 4)) * 4;
+                const int x = X0 + lx, y = Y0 + ly;
+                if (x < t.rtWidth && y < t.rtHeight) {
+                    uint4 *gp = (uint4 *)(g + (size_t)y * pitch + (size_t)x * 4);
+                    uint4 *sp = (uint4 *)(sm + (((ly >> 3) * BPR + (lx >> 3)) * 64 + (ly & 7) * 8 + (lx & 7)));
+                    if (STORE) *gp = *sp; else *sp = *gp;
+                }
+            }
+        } else {
+            for (int i = threadIdx.x; i < T * T; i += kTileThreads) {
+                const int ly = i / T, lx = i % T;
+                const int x = X0 + lx, y = Y0 + ly;
+                if (x < t.rtWidth && y < t.rtHeight) {
+                    uint32_t *gp = (uint32_t *)(g + (size_t)y * pitch + (size_t)x * 4);
+                    uint32_t *sp = sm + (((ly >> 3) * BPR + (lx >> 3)) * 64 + (ly & 7) * 8 + (lx & 7));
+                    if (STORE) *gp = *sp; else *sp = *gp;
+                }
+            }
+        }
+    }
+}
+
+// ---- the kernel -----------------------------------------------------------------------------------
+template <class PS, int MODE, int TLOG>
+__global__ void __launch_bounds__(kTileThreads, 2) tileKernel(const TileArgs t)
+{
+    typedef PsTraits<PS> TR;
+    typedef TileSmem<TLOG, TR::NRT> SM;
+    constexpr int T = SM::T, BPR = SM::BPR, NB = SM::NB, QW = SM::QW;
+
+    const int tx = blockIdx.x % t.tilesX, ty = blockIdx.x / t.tilesX;
+    if (!tileOwned(tx, ty, t.rank, t.world)) return;
+    if (*t.errorFlag & 1u) return;                           // geometry scratch exhausted: the draw is void
+
+    extern __shared__ __align__(16) char smem[];
+    char *rtSmem = smem;
+    uint64_t *sMasks = (uint64_t *)(smem + SM::offMasks);
+    uint32_t *sBlockmap = (uint32_t *)(smem + SM::offBlockmap);
+    uint32_t *qRec = (uint32_t *)(smem + SM::offQRec);
+    uint32_t *qRange = (uint32_t *)(smem + SM::offQRange);
+    uint32_t *qItem = (uint32_t *)(smem + SM::offQItem);
+    uint32_t *cGroup = (uint32_t *)(smem + SM::offChunkGroup);     // first group of each listed chunk
+    uint32_t *cPair = (uint32_t *)(smem + SM::offChunkPair);       // exclusive prefix of group counts
+    uint32_t *gList = (uint32_t *)(smem + SM::offGroupList);
+    uint64_t *sScan = (uint64_t *)(smem + SM::offScan);
+    Ctl *ctl = (Ctl *)(smem + SM::offCtl);
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int X0 = tx << TLOG, Y0 = ty << TLOG, X1 = X0 + T - 1, Y1 = Y0 + T - 1;
+    int phase = 0;
+    bool loaded = false;
+    uint32_t nGroup = 0, nQ = 0, nItems = 0;
+    unsigned long long frags = 0;
+
+    // ---- flush: coverage (A) + shading (B) of the queued primitives -----------------------------
+    auto flushQueue = [&]() {
+        if (nQ == 0) return;
+        if (tid == 0) qItem[nQ] = nItems;
+        for (int i = tid; i < NB * QW; i += kTileThreads) sBlockmap[i] = 0;
+        if (!loaded) {
+            moveTile<TLOG, TR::NRT, false>(t, rtSmem, X0, Y0);
+            loaded = true;
+        }
+        __syncthreads();
+
+        // A: one thread per (primitive, block) item
+        for (uint32_t it = tid; it < nItems; it += kTileThreads) {
+            uint32_t lo = 0, hi = nQ;                        // largest q with qItem[q] <= it
+            while (hi - lo > 1) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (qItem[mid] <= it) lo = mid; else hi = mid;
+            }
+            const uint32_t q = lo, rec = qRec[q], rg = qRange[q];
+            const int bx0 = rg & 0xff, by0 = (rg >> 8) & 0xff, nx = (int)((rg >> 16) & 0xff) - bx0 + 1;
+            const int li = (int)(it - qItem[q]);
+            const int bx = bx0 + li % nx, by = by0 + li / nx;
+            const int gx = X0 + bx * 8, gy = Y0 + by * 8;
+            uint64_t m;
+            if (MODE == SWR_DRAW_TRIANGLE) {
+                const float4 h2 = t.head[(size_t)rec * 3 + 2];
+                if (f2u(h2.y) & kModeSpan) {
+                    const float4 *sp = t.span + (size_t)rec * 3;
+                    m = coverSpan(sp[0], sp[1], sp[2], gx, gy, t.scMinX, t.scMaxX);
+                } else {
+                    m = coverBlock(t.head[(size_t)rec * 3], t.head[(size_t)rec * 3 + 1], h2, gx, gy);
+                }
+            } else if (MODE == SWR_DRAW_LINE) {
+                m = coverLine(t.head[(size_t)rec * 3], t.head[(size_t)rec * 3 + 1], gx, gy, t);
+            } else {
+                const float4 h0 = t.head[(size_t)rec * 3];
+                const int lx = f2i(h0.x) - gx, ly = f2i(h0.y) - gy;
+                m = ((unsigned)lx < 8u && (unsigned)ly < 8u) ? 1ull << (ly * 8 + lx) : 0ull;
+            }
+            sMasks[it] = m;
+            if (m) atomicOr(&sBlockmap[(by * BPR + bx) * QW + (q >> 5)], 1u << (q & 31));
+        }
+        __syncthreads();
+
+        // B: per block, in queue order, 32 fragments per round
+        PixelData p;
+        p.rtBase = rtSmem;
+        p.rtSlotStride = T * T * 4;
+        for (int b = wid; b < NB; b += kTileWarps) {
+            const int bx = b % BPR, by = b / BPR;
+            const int gx = X0 + bx * 8, gy = Y0 + by * 8;
+            const uint32_t bm = lane < QW ? sBlockmap[b * QW + lane] : 0u;
+            uint32_t wincl = __popc(bm);
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t n = __shfl_up_sync(0xffffffffu, wincl, o);
+                if (lane >= o) wincl += n;
+            }
+            const uint32_t wex = wincl - __popc(bm);
+            const uint32_t totalItems = __shfl_sync(0xffffffffu, wincl, 31);
+            for (uint32_t ibase = 0; ibase < totalItems; ibase += 32) {
+                // lane -> the (ibase + lane)-th item of this block
+                const uint32_t j = ibase + lane;
+                const bool ivalid = j < totalItems;
+                int wl = 0;
+#pragma unroll
+                for (int s = 16; s > 0; s >>= 1) {           // largest word wl with wex[wl] <= j
+                    const int c = wl + s;
+                    const uint32_t e = __shfl_sync(0xffffffffu, wex, c & 31);
+                    if (c < QW && e <= j) wl = c;
+                }
+                const uint32_t wbm = __shfl_sync(0xffffffffu, bm, wl);
+                const uint32_t wbase = __shfl_sync(0xffffffffu, wex, wl);
+                uint32_t q = 0, rec = 0;
+                uint64_t m = 0;
+                if (ivalid) {
+                    q = (uint32_t)wl * 32u + __fns(wbm, 0, (int)(j - wbase) + 1);
+                    rec = qRec[q];
+                    const uint32_t rg = qRange[q];
+                    const int bx0 = rg & 0xff, by0 = (rg >> 8) & 0xff, nx = (int)((rg >> 16) & 0xff) - bx0 + 1;
+                    m = sMasks[qItem[q] + (uint32_t)((by - by0) * nx + (bx - bx0))];
+                }
+                uint32_t fincl = __popcll(m);
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    uint32_t n = __shfl_up_sync(0xffffffffu, fincl, o);
+                    if (lane >= o) fincl += n;
+                }
+                const uint32_t fex = fincl - __popcll(m);
+                const uint32_t totalF = __shfl_sync(0xffffffffu, fincl, 31);
+                for (uint32_t fbase = 0; fbase < totalF; fbase += 32) {
+                    const uint32_t f = fbase + lane;
+                    const bool fvalid = f < totalF;
+                    int ol = 0;
+#pragma unroll
+                    for (int s = 16; s > 0; s >>= 1) {       // largest lane ol with fex[ol] <= f
+                        const int c = ol + s;
+                        const uint32_t e = __shfl_sync(0xffffffffu, fex, c & 31);
+                        if (c < 32 && e <= f) ol = c;
+                    }
+                    const uint64_t om = __shfl_sync(0xffffffffu, m, ol);
+                    const uint32_t orec = __shfl_sync(0xffffffffu, rec, ol);
+                    const uint32_t oex = __shfl_sync(0xffffffffu, fex, ol);
+                    const int bit = fvalid ? nthSetBit64(om, (int)(f - oex)) : 0;
+                    // fragments of different primitives on the same pixel run in emission order
+                    const int first = __shfl_sync(0xffffffffu, ol, 0);
+                    int rank = 0, maxRank = 0;
+                    if (!__all_sync(0xffffffffu, !fvalid || ol == first)) {
+                        const uint32_t peers = __match_any_sync(0xffffffffu, fvalid ? bit : 64 + lane);
+                        rank = __popc(peers & ((1u << lane) - 1u));
+                        maxRank = rank;
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) maxRank = max(maxRank, __shfl_xor_sync(0xffffffffu, maxRank, o));
+                    }
+                    const int xx = bit & 7, yy = bit >> 3;
+                    const bool onTarget = fvalid && gx + xx < t.rtWidth && gy + yy < t.rtHeight;
+                    p.rtOffset = (b * 64 + bit) * 4;
+                    for (int r = 0; r <= maxRank; ++r) {
+                        if (onTarget && rank == r) {
+                            if (MODE == SWR_DRAW_TRIANGLE) {
+                                shadeTriangleFragment<PS>(t, orec, gx, gy, xx, yy, p);
+                                ++frags;
+                            } else if (MODE == SWR_DRAW_LINE) {
+                                frags += shadeLineFragments<PS>(t, orec, gx + xx, gy + yy, p);
+                            } else {
+                                shadePointFragment<PS>(t, orec, gx + xx, gy + yy, p);
+                                ++frags;
+                            }
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        nQ = 0;
+        nItems = 0;
+    };
+
+    // ---- F3: records of the listed groups -> queue ------------------------------------------------
+    auto drainGroups = [&]() {
+        __syncthreads();                                     // gList writes of the caller are visible
+        const uint32_t npairs = nGroup * 32u;
+        for (uint32_t pb = 0; pb < npairs; pb += kTileThreads) {
+            const uint32_t pr = pb + tid;
+            bool hit = false;
+            uint32_t rec = 0, range = 0, items = 0;
+            if (pr < npairs) {
+                rec = gList[pr >> 5] * 32u + (pr & 31u);
+                const Box16 bb = t.bbox[rec];
+                if (boxOverlaps(bb, X0, Y0, X1, Y1)) {
+                    hit = true;
+                    const int bx0 = (max((int)bb.x0, X0) - X0) >> 3, by0 = (max((int)bb.y0, Y0) - Y0) >> 3;
+                    const int bx1 = (min((int)bb.x1, X1) - X0) >> 3, by1 = (min((int)bb.y1, Y1) - Y0) >> 3;
+                    range = (uint32_t)bx0 | ((uint32_t)by0 << 8) | ((uint32_t)bx1 << 16) | ((uint32_t)by1 << 24);
+                    items = (uint32_t)((bx1 - bx0 + 1) * (by1 - by0 + 1));
+                }
+            }
+            while (true) {
+                uint64_t total;
+                const uint64_t ex = blockScan(hit ? ((1ull << 32) | items) : 0ull, total, sScan, phase);
+                const uint32_t totHit = (uint32_t)(total >> 32), totItems = (uint32_t)total;
+                if (totHit == 0) break;
+                const uint32_t exHit = (uint32_t)(ex >> 32), exItems = (uint32_t)ex;
+                const bool fitsAll = nQ + totHit <= kQueue && nItems + totItems <= kItems;
+                const bool acc = hit && nQ + exHit < kQueue && nItems + exItems + items <= kItems;
+                if (acc) {
+                    qRec[nQ + exHit] = rec;
+                    qRange[nQ + exHit] = range;
+                    qItem[nQ + exHit] = nItems + exItems;
+                    hit = false;
+                }
+                if (fitsAll) {
+                    nQ += totHit;
+                    nItems += totItems;
+                    break;
+                }
+                // queue full: count what was accepted, flush, retry the rest
+                if (tid == 0) { ctl->accQ = 0; ctl->accItems = 0; }
+                __syncthreads();
+                if (acc) { atomicAdd(&ctl->accQ, 1u); atomicAdd(&ctl->accItems, items); }
+                __syncthreads();
+                nQ += ctl->accQ;
+                nItems += ctl->accItems;
+                __syncthreads();
+                flushQueue();
+            }
+        }
+        __syncthreads();
+        nGroup = 0;
+    };
+
+    // ---- F1 + F2 ----------------------------------------------------------------------------------
+    const uint32_t *row = t.tilemap + (size_t)blockIdx.x * t.chunkWords;
+    for (int wb = 0; wb < t.chunkWords; wb += kTileThreads) {
+        uint32_t pending = (wb + tid < t.chunkWords) ? row[wb + tid] : 0u;
+        while (true) {
+            // F1: this step's set bits -> chunk list {first group, group count}
+            uint32_t myGroups = 0;
+            {
+                uint32_t bits = pending;
+                while (bits) {
+                    const int bpos = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    const uint32_t c = (uint32_t)(wb + tid) * 32u + (uint32_t)bpos;
+                    uint32_t cnt;
+                    if (c & 1u) cnt = t.extra[c >> 1].y;
+                    else cnt = (uint32_t)min(kBatch, t.numPrims - (int)(c >> 1) * kBatch);
+                    myGroups += (cnt + 31u) >> 5;
+                }
+            }
+            uint64_t total;
+            const uint64_t ex = blockScan(((uint64_t)__popc(pending) << 32) | myGroups, total, sScan, phase);
+            const uint32_t totChunks = (uint32_t)(total >> 32);
+            if (totChunks == 0) break;
+            uint32_t ci = (uint32_t)(ex >> 32), pairBase = (uint32_t)ex;
+            while (pending && ci < kChunkList) {
+                const int bpos = __ffs(pending) - 1;
+                pending &= pending - 1;
+                const uint32_t c = (uint32_t)(wb + tid) * 32u + (uint32_t)bpos;
+                uint32_t cnt, g0;
+                if (c & 1u) { const uint2 e = t.extra[c >> 1]; g0 = e.x >> 5; cnt = e.y; }
+                else { g0 = (c >> 1) * (kBatch / 32); cnt = (uint32_t)min(kBatch, t.numPrims - (int)(c >> 1) * kBatch); }
+                cGroup[ci] = g0;
+                cPair[ci] = pairBase;
+                pairBase += (cnt + 31u) >> 5;
+                ++ci;
+                if (ci == min(totChunks, (uint32_t)kChunkList)) cPair[ci] = pairBase;   // sentinel by the last writer
+            }
+            __syncthreads();
+            const uint32_t nChunk = min(totChunks, (uint32_t)kChunkList);
+            const uint32_t npairs = cPair[nChunk];
+
+            // F2: group boxes of the listed chunks -> group list
+            for (uint32_t pb = 0; pb < npairs; pb += kTileThreads) {
+                if (nGroup + kTileThreads > kGroupList) drainGroups();
+                const uint32_t pr = pb + tid;
+                bool hit = false;
+                uint32_t grp = 0;
+                if (pr < npairs) {
+                    uint32_t lo = 0, hi = nChunk;            // largest chunk entry with cPair[entry] <= pr
+                    while (hi - lo > 1) {
+                        const uint32_t mid = (lo + hi) >> 1;
+                        if (cPair[mid] <= pr) lo = mid; else hi = mid;
+                    }
+                    grp = cGroup[lo] + (pr - cPair[lo]);
+                    hit = boxOverlaps(t.gbox[grp], X0, Y0, X1, Y1);
+                }
+                uint64_t tot2;
+                const uint64_t ex2 = blockScan(hit ? 1ull : 0ull, tot2, sScan, phase);
+                if (hit) gList[nGroup + (uint32_t)ex2] = grp;
+                nGroup += (uint32_t)tot2;
+            }
+            __syncthreads();
+            if (totChunks <= kChunkList) break;
+        }
+    }
+    drainGroups();
+    flushQueue();
+
+    if (loaded) moveTile<TLOG, TR::NRT, true>(t, rtSmem, X0, Y0);
+
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) frags += __shfl_xor_sync(0xffffffffu, frags, o);
+    if (lane == 0 && frags) atomicAdd(t.fragCounter, frags);
+}
+
+template <class PS, int MODE, int TLOG>
+void launchTiles(const void *args, void *stream)
+{
+    typedef TileSmem<TLOG, PsTraits<PS>::NRT> SM;
+    const TileArgs *t = static_cast<const TileArgs *>(args);
+    cudaFuncSetAttribute(tileKernel<PS, MODE, TLOG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::bytes);
+    tileKernel<PS, MODE, TLOG><<<t->tilesX * t->tilesY, kTileThreads, SM::bytes, (cudaStream_t)stream>>>(*t);
+}
+
+template <class PS>
+const swr_pixel_shader *pixelShaderBinding(const char *name = "user")
+{
+    static const swr_pixel_shader d = {
+        { { &launchTiles<PS, 0, 5>, &launchTiles<PS, 0, 6> },
+          { &launchTiles<PS, 1, 5>, &launchTiles<PS, 1, 6> },
+          { &launchTiles<PS, 2, 5>, &launchTiles<PS, 2, 6> } },
+        &uploadUniforms,
+        PS::AVarCount, PS::PVarCount, PS::InterpolateZ ? 1 : 0, PS::InterpolateW ? 1 : 0,
+        PS::RenderTargets, name };
+    return &d;
+}
+
+} // namespace detail
+} // namespace swr
+
+#endif // __CUDACC__

@@ -25,6 +25,7 @@
 extern "C" {
 #endif
 
+#ifndef SWR_B200_H   /* (tests/hostcheck includes both headers; the ids are identical) */
 /* Stock vertex shaders (mirrored 1:1 by softwarerenderer_b200/csrc/stock_shaders.cuh). */
 enum {
     SWR_VS_POS_COLOR = 0,     /* {x,y,z,r,g,b}: pos passthrough, w=1, 3 avars   (Benchmark.cpp:38-48)   */
@@ -41,6 +42,7 @@ enum {
     SWR_PS_VARY_DUMP = 4,     /* Z, W, A=3, P=2: vary[k][i] = z,w,invw,a0,a1,a2,p0,p1; count[i]++           */
     SWR_PS_TEXTURED = 5       /* W, A=3, P=2: color[i] = texture[nearest(u,v) wrapped]     (Box.cpp:39-62) */
 };
+#endif
 
 /* Emission ordinal of a primitive: batch * SWR_ORDINAL_STRIDE + slot, where batch
  * counts the 1024-primitive flushes of VertexProcessor.cpp:110-116 and slot is the
@@ -49,8 +51,10 @@ enum {
  * most a 9-gon in general position, but PolyClipper.cpp:64-74 duplicates vertices that lie
  * exactly on a plane, so both checkers and the CUDA path allow SWR_MAX_POLY = 12 vertices
  * (10 fan triangles); 10240 = 1024 * 10 is then the largest slot count of one batch. */
+#ifndef SWR_MAX_POLY
 #define SWR_MAX_POLY 12
 #define SWR_ORDINAL_STRIDE 10240u
+#endif
 #define SWR_VARY_PLANES 8
 
 typedef struct swr_scene {

@@ -1,0 +1,861 @@
+// runtime.cu -- the shader-agnostic runtime behind the C ABI (include/swr_b200.h): contexts,
+// device scratch, host-pointer staging, pass planning, kernel orchestration, measurement, the
+// raster-list entry (IRasterizer::draw*List) and the tile pack / unpack kernels of the
+// multi-GPU composite.  Shader-templated kernels live in include/swr/detail/{geometry,tile}.cuh
+// and reach this file only as launcher thunks (swr_vertex_shader / swr_pixel_shader).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <swr_b200.h>
+#include <swr/detail/common.h>
+#include <swr/detail/geometry.cuh>
+
+using namespace swr::detail;
+
+namespace {
+
+thread_local std::string g_lastError;
+
+int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_lastError = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                             \
+    do {                                                                                           \
+        cudaError_t e__ = (expr);                                                                  \
+        if (e__ != cudaSuccess) return fail(-100, "%s: %s", #expr, cudaGetErrorString(e__));       \
+    } while (0)
+
+struct DevBuf {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+    int reserve(size_t need)
+    {
+        if (need <= bytes) return 0;
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        bytes = 0;
+        size_t want = need + need / 8;
+        cudaError_t e = cudaMalloc(&ptr, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            e = cudaMalloc(&ptr, need);
+            want = need;
+        }
+        if (e != cudaSuccess) return fail(-101, "cudaMalloc(%zu bytes): %s", need, cudaGetErrorString(e));
+        bytes = want;
+        return 0;
+    }
+    void release()
+    {
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        bytes = 0;
+    }
+};
+
+struct Attrib {
+    const void *ptr = nullptr;
+    int stride = 0;
+    size_t bytes = 0;
+};
+
+struct Counters {               // one small device block
+    uint32_t extraAlloc;
+    uint32_t errorFlag;         // per draw: bit 0 voids the draw (tile kernel exits)
+    uint32_t stickyFlag;        // same bits, accumulated until swr_finish reports them
+    uint32_t pad;
+    unsigned long long fragments;
+};
+
+bool isDevicePointer(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+} // namespace
+
+struct swr_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t evGeom0 = nullptr, evGeom1 = nullptr, evTile1 = nullptr, evTimer0 = nullptr, evTimer1 = nullptr;
+    bool haveDrawEvents = false;
+
+    // VertexProcessor state (defaults VertexProcessor.cpp:29-35)
+    int vpX = 0, vpY = 0, vpW = 0, vpH = 0;
+    float px = 0, py = 0, ox = 0, oy = 0;
+    float depthN = 0.0f, depthF = 1.0f;
+    int cullMode = SWR_CULL_CW;
+    Attrib attribs[SWR_MAX_VERTEX_ATTRIBS];
+    const swr_vertex_shader *vs = nullptr;
+    // Rasterizer state (defaults Rasterizer.h:67-72)
+    int rasterMode = SWR_RASTER_SPAN;
+    int scMinX = 0, scMinY = 0, scMaxX = 0, scMaxY = 0;
+    const swr_pixel_shader *ps = nullptr;
+    // additive state
+    RenderTargetDesc rt[SWR_MAX_RENDER_TARGETS] = {};
+    int rtW = 0, rtH = 0;
+    unsigned char uniforms[SWR_MAX_UNIFORM_BYTES] = {};
+    size_t uniformBytes = 0;
+    int tileSizeReq = 0, rank = 0, world = 1;
+    size_t scratchLimit = (size_t)16 << 30;
+
+    // scratch
+    DevBuf bbox, gbox, head, params, span, tilemap, extra, counters, dbgVerts, stageIdx, l2flush, ownedIdx;
+    bool countersInit = false;
+    int ownedKey[5] = { 0, 0, 0, 0, 0 };   // {tile size, rank, world, width, height} of ownedIdx
+    DevBuf stageAttrib[SWR_MAX_VERTEX_ATTRIBS];
+    uint32_t *hostFlags = nullptr;   // pinned: error flag read-back
+    bool debugStream = false;
+
+    // last pass (debug reader)
+    int lastPassPrims = 0, lastDrawMode = 0;
+    uint32_t lastFirstBatch = 0;
+    uint32_t lastExtrasBegin = 0;
+
+    swr_stats stats = {};
+};
+
+namespace {
+
+int setDevice(swr_context *c)
+{
+    CUDA_TRY(cudaSetDevice(c->device));
+    return 0;
+}
+
+size_t scratchBytes(const swr_context *c)
+{
+    size_t n = c->bbox.bytes + c->gbox.bytes + c->head.bytes + c->params.bytes + c->span.bytes + c->tilemap.bytes +
+               c->extra.bytes + c->counters.bytes + c->dbgVerts.bytes + c->stageIdx.bytes + c->l2flush.bytes + c->ownedIdx.bytes;
+    for (int i = 0; i < SWR_MAX_VERTEX_ATTRIBS; ++i) n += c->stageAttrib[i].bytes;
+    return n;
+}
+
+// ---- raster-list entry: IRasterizer::draw{Point,Line,Triangle}List on screen-space vertices -------
+// Rasterizer.h:116-141: primitives whose FIRST index is -1 are skipped; no clipping, transform or
+// culling happens here (that was the VertexProcessor's job).
+__global__ void __launch_bounds__(kGeomThreads) rasterListKernel(const GeomArgs g)
+{
+    typedef CVert<SWR_MAX_AVARS, SWR_MAX_PVARS> V;
+    const int tid = threadIdx.x;
+    const int batch = blockIdx.x;
+    const int primBase = batch * kBatch;
+    const int cnt = min(kBatch, g.numPrims - primBase);
+    const uint32_t ord0 = (g.firstBatch + (uint32_t)batch) * SWR_ORDINAL_STRIDE;
+    const int per = g.drawMode + 1;
+    const V *verts = static_cast<const V *>(g.rasterVerts);     // RasterizerVertex has exactly this layout
+    for (int r = 0; r < kBatch / kGeomThreads; ++r) {
+        const int slot = r * kGeomThreads + tid;
+        const uint32_t rec = (uint32_t)(primBase + slot);
+        Box16 box = deadBox();
+        if (slot < cnt) {
+            const int32_t *ip = g.indices + (size_t)rec * per;
+            const uint32_t ordinal = ord0 + (uint32_t)slot;
+            if (ip[0] != -1) {
+                if (g.drawMode == SWR_DRAW_TRIANGLE)
+                    box = emitScreenTriangle<SWR_MAX_AVARS, SWR_MAX_PVARS>(g, rec, ordinal, false, verts[ip[0]], verts[ip[1]], verts[ip[2]]);
+                else if (g.drawMode == SWR_DRAW_LINE)
+                    box = emitScreenLine<SWR_MAX_AVARS, SWR_MAX_PVARS>(g, rec, ordinal, verts[ip[0]], verts[ip[1]]);
+                else
+                    box = emitScreenPoint<SWR_MAX_AVARS, SWR_MAX_PVARS>(g, rec, ordinal, verts[ip[0]]);
+            }
+        }
+        g.bbox[rec] = box;
+        publishGroup(g, box, rec >> 5, 2u * (uint32_t)batch);
+    }
+    if (tid == 0) g.extra[batch] = make_uint2(0u, 0u);
+}
+
+void launchRasterList(const void *args, void *stream)
+{
+    const GeomArgs *g = static_cast<const GeomArgs *>(args);
+    const int batches = (g->numPrims + kBatch - 1) / kBatch;
+    if (batches > 0) rasterListKernel<<<batches, kGeomThreads, 0, (cudaStream_t)stream>>>(*g);
+}
+
+// ---- multi-GPU composite helpers ---------------------------------------------------------------------
+// Tile-major exchange buffer: the owned tiles of one rank in increasing tile id, T*T words each,
+// row-major inside a tile.  One CTA per owned tile, 128-bit moves.
+template <bool PACK>
+__global__ void tileExchangeKernel(char *surface, int pitch, int width, int height, int tileShift, int tilesX, int tilesY,
+                                   int rank, int world, const int *ownedIndex, uint32_t *buf)
+{
+    const int tile = blockIdx.x;
+    const int tx = tile % tilesX, ty = tile / tilesX;
+    if (!tileOwned(tx, ty, rank, world)) return;
+    const int T = 1 << tileShift;
+    uint32_t *tb = buf + (size_t)ownedIndex[tile] * T * T;
+    const bool vec = ((((uintptr_t)surface) | (uintptr_t)pitch) & 15) == 0 && (width & 3) == 0;
+    if (vec) {
+        for (int i = threadIdx.x; i < T * T / 4; i += blockDim.x) {
+            const int ly = i / (T / 4), lx = (i % (T / 4)) * 4;
+            const int x = (tx << tileShift) + lx, y = (ty << tileShift) + ly;
+            uint4 *bp = (uint4 *)(tb + ly * T + lx);
+            if (x < width && y < height) {
+                uint4 *gp = (uint4 *)(surface + (size_t)y * pitch + (size_t)x * 4);
+                if (PACK) *bp = *gp; else *gp = *bp;
+            } else if (PACK) {
+                *bp = make_uint4(0, 0, 0, 0);
+            }
+        }
+    } else {
+        for (int i = threadIdx.x; i < T * T; i += blockDim.x) {
+            const int ly = i / T, lx = i % T;
+            const int x = (tx << tileShift) + lx, y = (ty << tileShift) + ly;
+            if (x < width && y < height) {
+                uint32_t *gp = (uint32_t *)(surface + (size_t)y * pitch + (size_t)x * 4);
+                if (PACK) tb[ly * T + lx] = *gp; else *gp = tb[ly * T + lx];
+            } else if (PACK) {
+                tb[ly * T + lx] = 0;
+            }
+        }
+    }
+}
+
+__global__ void fill32Kernel(uint32_t *dst, uint32_t value, size_t count)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < count; i += stride) dst[i] = value;
+}
+
+int chooseTileShift(const swr_context *c, int renderTargets)
+{
+    auto fits64 = [&]() { return (size_t)renderTargets * 64 * 64 * 4 + 48 * 1024 <= (size_t)227 * 1024; };
+    int req = c->tileSizeReq;
+    if (req == 0) {
+        const char *env = getenv("SWR_TILE_SIZE");
+        if (env) req = atoi(env);
+    }
+    if (req == 64 && fits64()) return 6;
+    if (req == 32) return 5;
+    const long tiles64 = (long)((c->rtW + 63) / 64) * ((c->rtH + 63) / 64);
+    return (tiles64 >= 1024 && fits64()) ? 6 : 5;
+}
+
+// One draw = one or more passes of {geometry kernel, tile kernel}.
+int drawCommon(swr_context *c, int drawMode, size_t count, const int32_t *indices, const void *rasterVerts, size_t rasterVertCount)
+{
+    if (int rc = setDevice(c)) return rc;
+    if (drawMode < 0 || drawMode > 2) return fail(-2, "bad draw mode %d", drawMode);
+    const swr_pixel_shader *ps = c->ps;
+    const swr_vertex_shader *vs = c->vs;
+    if (!ps) return fail(-3, "no pixel shader set");
+    if (!rasterVerts && !vs) return fail(-3, "no vertex shader set");
+    const int per = drawMode + 1;
+    const size_t nprims = count / per;
+    c->stats.draws++;
+    c->stats.primitives_in += nprims;
+    if (nprims == 0) return 0;
+    if (nprims > (size_t)0x7fffffff / 4) return fail(-4, "too many primitives in one draw (%zu)", nprims);
+    if (c->rtW <= 0 || c->rtH <= 0) return fail(-5, "no render target registered (swr_set_render_target)");
+    if (c->rtW > 32767 || c->rtH > 32767) return fail(-5, "render target too large");
+    for (int s = 0; s < ps->render_targets; ++s)
+        if (!c->rt[s].ptr) return fail(-5, "pixel shader '%s' stages render target slots [0,%d) but slot %d is not registered", ps->name, ps->render_targets, s);
+    if (c->scMinX < 0 || c->scMinY < 0) return fail(-6, "scissor origin must be >= 0");
+    if (!rasterVerts) {
+        if (ps->avar_count > vs->avar_count || ps->pvar_count > vs->pvar_count)
+            return fail(-7, "pixel shader '%s' interpolates more variables than vertex shader '%s' outputs", ps->name, vs->name);
+        for (int i = 0; i < vs->attrib_count; ++i)
+            if (!c->attribs[i].ptr) return fail(-8, "vertex attribute %d not set", i);
+    }
+
+    // ---- inputs: device memory in place, host memory staged
+    GeomArgs g;
+    memset(&g, 0, sizeof(g));
+    const int32_t *devIndices = indices;
+    if (!isDevicePointer(indices)) {
+        if (int rc = c->stageIdx.reserve(count * sizeof(int32_t))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(c->stageIdx.ptr, indices, nprims * per * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+        devIndices = static_cast<const int32_t *>(c->stageIdx.ptr);
+    }
+    if (rasterVerts) {
+        const void *dv = rasterVerts;
+        if (!isDevicePointer(rasterVerts)) {
+            const size_t bytes = rasterVertCount * 144;
+            if (int rc = c->stageAttrib[0].reserve(bytes)) return rc;
+            CUDA_TRY(cudaMemcpyAsync(c->stageAttrib[0].ptr, rasterVerts, bytes, cudaMemcpyHostToDevice, c->stream));
+            dv = c->stageAttrib[0].ptr;
+        }
+        g.rasterVerts = dv;
+    } else {
+        for (int i = 0; i < vs->attrib_count; ++i) {
+            const Attrib &a = c->attribs[i];
+            const void *dp = a.ptr;
+            if (!isDevicePointer(a.ptr)) {
+                if (a.bytes == 0) return fail(-9, "vertex attribute %d is host memory: its extent is required (bytes > 0)", i);
+                if (int rc = c->stageAttrib[i].reserve(a.bytes)) return rc;
+                CUDA_TRY(cudaMemcpyAsync(c->stageAttrib[i].ptr, a.ptr, a.bytes, cudaMemcpyHostToDevice, c->stream));
+                dp = c->stageAttrib[i].ptr;
+            }
+            g.attribPtr[i] = dp;
+            g.attribStride[i] = a.stride;
+        }
+    }
+
+    // ---- uniforms into the shader TUs' constant blocks
+    if (c->uniformBytes) {
+        if (!rasterVerts && vs->set_uniforms && vs->set_uniforms(c->uniforms, c->uniformBytes, c->stream) != 0)
+            return fail(-10, "uniform upload failed (vertex shader '%s')", vs->name);
+        if (ps->set_uniforms && (rasterVerts || ps->set_uniforms != vs->set_uniforms) &&
+            ps->set_uniforms(c->uniforms, c->uniformBytes, c->stream) != 0)
+            return fail(-10, "uniform upload failed (pixel shader '%s')", ps->name);
+    }
+
+    // ---- pass plan
+    const int tileShift = chooseTileShift(c, ps->render_targets);
+    const int T = 1 << tileShift;
+    const int tilesX = (c->rtW + T - 1) / T, tilesY = (c->rtH + T - 1) / T;
+    const int nA = ps->avar_count, nP = ps->pvar_count, useZ = ps->interpolate_z, useW = ps->interpolate_w;
+    const int paramStride = paramFloats(drawMode, nA, nP, useZ, useW);
+    const bool needSpan = drawMode == SWR_DRAW_TRIANGLE && c->rasterMode != SWR_RASTER_BLOCK;
+    const bool tri = drawMode == SWR_DRAW_TRIANGLE && !rasterVerts;
+    const size_t recBytes = sizeof(Box16) + 48 + (size_t)paramStride * 4 + (needSpan ? 48 : 0) + (c->debugStream ? 48 : 0);
+    const size_t perPrimWorst = recBytes * (tri ? (size_t)(1 + kMaxFan - 1) : 1) + 16;
+    size_t passPrims = c->scratchLimit / perPrimWorst;
+    passPrims = std::max<size_t>(kBatch, passPrims / kBatch * kBatch);
+    passPrims = std::min(passPrims, (nprims + kBatch - 1) / kBatch * kBatch);
+    const size_t firstsCap = passPrims;                                  // multiple of kBatch
+    const size_t extrasCap = tri ? passPrims * (size_t)(kMaxFan - 1) : 0;
+    const size_t recCap = firstsCap + extrasCap;
+    if (recCap > 0xfffffff0u) return fail(-4, "pass too large");
+    const size_t passBatches = passPrims / kBatch;
+    const int chunkWords = (int)((2 * passBatches + 31) / 32);
+
+    if (int rc = c->bbox.reserve(recCap * sizeof(Box16))) return rc;
+    if (int rc = c->gbox.reserve((recCap / kGroup + 1) * sizeof(Box16))) return rc;
+    if (int rc = c->head.reserve(recCap * 48)) return rc;
+    if (int rc = c->params.reserve(recCap * (size_t)paramStride * 4 + 16)) return rc;
+    if (needSpan) if (int rc = c->span.reserve(recCap * 48)) return rc;
+    if (int rc = c->tilemap.reserve((size_t)tilesX * tilesY * chunkWords * 4)) return rc;
+    if (int rc = c->extra.reserve(passBatches * sizeof(uint2))) return rc;
+    if (int rc = c->counters.reserve(sizeof(Counters))) return rc;
+    if (c->debugStream) if (int rc = c->dbgVerts.reserve(recCap * 48)) return rc;
+    if (!c->hostFlags) {
+        CUDA_TRY(cudaMallocHost((void **)&c->hostFlags, 64));
+        c->hostFlags[0] = 0;
+    }
+    c->stats.scratch_bytes = scratchBytes(c);
+
+    Counters *dc = static_cast<Counters *>(c->counters.ptr);
+    if (!c->countersInit) {
+        CUDA_TRY(cudaMemsetAsync(dc, 0, sizeof(Counters), c->stream));
+        c->countersInit = true;
+    }
+    CUDA_TRY(cudaMemsetAsync(&dc->errorFlag, 0, sizeof(uint32_t), c->stream));
+
+    g.drawMode = drawMode;
+    g.px = c->px; g.py = c->py; g.ox = c->ox; g.oy = c->oy;
+    g.depthN = c->depthN; g.depthF = c->depthF;
+    g.cullMode = c->cullMode; g.rasterMode = c->rasterMode;
+    g.scMinX = c->scMinX; g.scMinY = c->scMinY; g.scMaxX = c->scMaxX; g.scMaxY = c->scMaxY;
+    g.nA = nA; g.nP = nP; g.useZ = useZ; g.useW = useW;
+    g.bbox = static_cast<Box16 *>(c->bbox.ptr);
+    g.gbox = static_cast<Box16 *>(c->gbox.ptr);
+    g.head = static_cast<float4 *>(c->head.ptr);
+    g.params = static_cast<float *>(c->params.ptr);
+    g.span = static_cast<float4 *>(c->span.ptr);
+    g.paramStride = paramStride;
+    g.tilemap = static_cast<uint32_t *>(c->tilemap.ptr);
+    g.chunkWords = chunkWords;
+    g.tileShift = tileShift;
+    g.tilesX = tilesX; g.tilesY = tilesY;
+    g.extra = static_cast<uint2 *>(c->extra.ptr);
+    g.extraAlloc = &dc->extraAlloc;
+    g.extrasEnd = (uint32_t)recCap;
+    g.errorFlag = &dc->errorFlag;
+    g.dbgVerts = c->debugStream ? static_cast<float *>(c->dbgVerts.ptr) : nullptr;
+
+    TileArgs t;
+    memset(&t, 0, sizeof(t));
+    t.bbox = g.bbox; t.gbox = g.gbox; t.head = g.head; t.params = g.params; t.span = g.span;
+    t.paramStride = paramStride;
+    t.tilemap = g.tilemap; t.chunkWords = chunkWords;
+    t.extra = g.extra;
+    t.tilesX = tilesX; t.tilesY = tilesY;
+    t.rank = c->rank; t.world = c->world;
+    t.rtWidth = c->rtW; t.rtHeight = c->rtH;
+    t.numRT = ps->render_targets;
+    for (int s = 0; s < SWR_MAX_RENDER_TARGETS; ++s) t.rt[s] = c->rt[s];
+    t.scMinX = c->scMinX; t.scMinY = c->scMinY; t.scMaxX = c->scMaxX; t.scMaxY = c->scMaxY;
+    t.fragCounter = &dc->fragments;
+    t.errorFlag = &dc->errorFlag;
+
+    swr_launch_fn geomLaunch = rasterVerts ? &launchRasterList : vs->launch_geometry;
+    swr_launch_fn tileLaunch = ps->launch_tiles[drawMode][tileShift - 5];
+    const uint32_t extrasBegin = (uint32_t)firstsCap;
+
+    CUDA_TRY(cudaEventRecord(c->evGeom0, c->stream));
+    for (size_t first = 0; first < nprims; first += passPrims) {
+        const size_t n = std::min(passPrims, nprims - first);
+        g.indices = devIndices + first * per;
+        g.numPrims = (int)n;
+        g.firstBatch = (uint32_t)(first / kBatch);
+        t.numPrims = (int)n;
+        t.numChunks = (int)(2 * ((n + kBatch - 1) / kBatch));
+        CUDA_TRY(cudaMemsetAsync(c->tilemap.ptr, 0, (size_t)tilesX * tilesY * chunkWords * 4, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(&dc->extraAlloc, &extrasBegin, sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+        if (c->debugStream) CUDA_TRY(cudaMemsetAsync(c->dbgVerts.ptr, 0xff, recCap * 48, c->stream));
+        geomLaunch(&g, c->stream);
+        if (first + passPrims >= nprims) CUDA_TRY(cudaEventRecord(c->evGeom1, c->stream));
+        tileLaunch(&t, c->stream);
+        c->stats.kernel_launches += 2;
+        c->stats.passes++;
+        c->lastPassPrims = (int)n;
+        c->lastFirstBatch = g.firstBatch;
+    }
+    CUDA_TRY(cudaEventRecord(c->evTile1, c->stream));
+    CUDA_TRY(cudaGetLastError());
+    c->haveDrawEvents = true;
+    c->lastDrawMode = drawMode;
+    c->lastExtrasBegin = extrasBegin;
+    c->stats.last_tile_size = T;
+    return 0;
+}
+
+} // namespace
+
+// =============================================================================================== C ABI
+extern "C" {
+
+int swr_abi_version(void) { return 1; }
+const char *swr_last_error(void) { return g_lastError.c_str(); }
+
+int swr_create(swr_context **out, int cuda_device)
+{
+    if (!out) return fail(-1, "null out pointer");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(-20, "no CUDA device: this library has no CPU fallback");
+    }
+    if (cuda_device < 0 || cuda_device >= ndev) return fail(-21, "bad CUDA device %d (have %d)", cuda_device, ndev);
+    swr_context *c = new swr_context();
+    c->device = cuda_device;
+    cudaError_t e = cudaSetDevice(cuda_device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    cudaEvent_t *evs[] = { &c->evGeom0, &c->evGeom1, &c->evTile1, &c->evTimer0, &c->evTimer1 };
+    for (cudaEvent_t *ev : evs)
+        if (e == cudaSuccess) e = cudaEventCreate(ev);
+    if (e != cudaSuccess) {
+        delete c;
+        return fail(-22, "context creation: %s", cudaGetErrorString(e));
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, cuda_device) == cudaSuccess && prop.major < 10) {
+        swr_destroy(c);
+        return fail(-23, "device %d is sm_%d%d; this library is built for sm_100a only", cuda_device, prop.major, prop.minor);
+    }
+    *out = c;
+    return 0;
+}
+
+void swr_destroy(swr_context *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    DevBuf *bufs[] = { &c->bbox, &c->gbox, &c->head, &c->params, &c->span, &c->tilemap, &c->extra, &c->counters,
+                       &c->dbgVerts, &c->stageIdx, &c->l2flush, &c->ownedIdx };
+    for (DevBuf *b : bufs) b->release();
+    for (int i = 0; i < SWR_MAX_VERTEX_ATTRIBS; ++i) c->stageAttrib[i].release();
+    if (c->hostFlags) cudaFreeHost(c->hostFlags);
+    cudaEvent_t evs[] = { c->evGeom0, c->evGeom1, c->evTile1, c->evTimer0, c->evTimer1 };
+    for (cudaEvent_t ev : evs)
+        if (ev) cudaEventDestroy(ev);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int swr_set_viewport(swr_context *c, int x, int y, int width, int height)
+{
+    if (!c) return fail(-1, "null context");
+    c->vpX = x; c->vpY = y; c->vpW = width; c->vpH = height;
+    c->px = width / 2.0f;                                   // VertexProcessor.cpp:50-53
+    c->py = height / 2.0f;
+    c->ox = (x + c->px);
+    c->oy = (y + c->py);
+    return 0;
+}
+
+int swr_set_depth_range(swr_context *c, float n, float f)
+{
+    if (!c) return fail(-1, "null context");
+    c->depthN = n; c->depthF = f;
+    return 0;
+}
+
+int swr_set_cull_mode(swr_context *c, int mode)
+{
+    if (!c) return fail(-1, "null context");
+    if (mode < 0 || mode > 2) return fail(-2, "bad cull mode %d", mode);
+    c->cullMode = mode;
+    return 0;
+}
+
+int swr_set_vertex_attrib_pointer(swr_context *c, int index, int stride, const void *buffer, size_t bytes)
+{
+    if (!c) return fail(-1, "null context");
+    if (index < 0 || index >= SWR_MAX_VERTEX_ATTRIBS) return fail(-2, "attribute index %d out of range", index);   // assert at VertexProcessor.cpp:69
+    c->attribs[index].ptr = buffer;
+    c->attribs[index].stride = stride;
+    c->attribs[index].bytes = bytes;
+    return 0;
+}
+
+int swr_set_vertex_shader(swr_context *c, const swr_vertex_shader *vs)
+{
+    if (!c || !vs) return fail(-1, "null argument");
+    if (vs->attrib_count > SWR_MAX_VERTEX_ATTRIBS) return fail(-2, "AttribCount %d > %d", vs->attrib_count, SWR_MAX_VERTEX_ATTRIBS);  // VertexProcessor.h:80
+    c->vs = vs;
+    return 0;
+}
+
+int swr_set_raster_mode(swr_context *c, int mode)
+{
+    if (!c) return fail(-1, "null context");
+    if (mode < 0 || mode > 2) return fail(-2, "bad raster mode %d", mode);
+    c->rasterMode = mode;
+    return 0;
+}
+
+int swr_set_scissor_rect(swr_context *c, int x, int y, int width, int height)
+{
+    if (!c) return fail(-1, "null context");
+    c->scMinX = x; c->scMinY = y;                           // Rasterizer.h:81-87
+    c->scMaxX = x + width; c->scMaxY = y + height;
+    return 0;
+}
+
+int swr_set_pixel_shader(swr_context *c, const swr_pixel_shader *ps)
+{
+    if (!c || !ps) return fail(-1, "null argument");
+    if (ps->render_targets > SWR_MAX_RENDER_TARGETS) return fail(-2, "RenderTargets %d > %d", ps->render_targets, SWR_MAX_RENDER_TARGETS);
+    c->ps = ps;
+    return 0;
+}
+
+int swr_set_render_target(swr_context *c, int slot, void *device_ptr, int pitch_bytes, int width, int height)
+{
+    if (!c) return fail(-1, "null context");
+    if (slot < 0 || slot >= SWR_MAX_RENDER_TARGETS) return fail(-2, "render target slot %d out of range", slot);
+    if (device_ptr) {
+        if (!isDevicePointer(device_ptr)) return fail(-2, "render target %d is not device memory", slot);
+        if (width <= 0 || height <= 0 || pitch_bytes < width * 4 || (pitch_bytes & 3)) return fail(-2, "bad render target geometry");
+        c->rtW = width;
+        c->rtH = height;
+    }
+    c->rt[slot].ptr = device_ptr;
+    c->rt[slot].pitch = pitch_bytes;
+    return 0;
+}
+
+int swr_set_uniforms(swr_context *c, const void *data, size_t bytes)
+{
+    if (!c) return fail(-1, "null context");
+    if (bytes > SWR_MAX_UNIFORM_BYTES) return fail(-2, "uniform block of %zu bytes exceeds %d", bytes, SWR_MAX_UNIFORM_BYTES);
+    if (bytes) memcpy(c->uniforms, data, bytes);
+    c->uniformBytes = bytes;
+    return 0;
+}
+
+int swr_set_tile_size(swr_context *c, int tile_size)
+{
+    if (!c) return fail(-1, "null context");
+    if (tile_size != 0 && tile_size != 32 && tile_size != 64) return fail(-2, "tile size must be 0, 32 or 64");
+    c->tileSizeReq = tile_size;
+    return 0;
+}
+
+int swr_set_tile_partition(swr_context *c, int rank, int world)
+{
+    if (!c) return fail(-1, "null context");
+    if (world < 1 || rank < 0 || rank >= world) return fail(-2, "bad partition %d/%d", rank, world);
+    c->rank = rank;
+    c->world = world;
+    return 0;
+}
+
+int swr_set_scratch_limit(swr_context *c, size_t bytes)
+{
+    if (!c) return fail(-1, "null context");
+    c->scratchLimit = std::max<size_t>(bytes, (size_t)64 << 20);
+    return 0;
+}
+
+int swr_draw_elements(swr_context *c, int draw_mode, size_t count, const int32_t *indices)
+{
+    if (!c) return fail(-1, "null context");
+    if (count && !indices) return fail(-1, "null indices");
+    return drawCommon(c, draw_mode, count, indices, nullptr, 0);
+}
+
+int swr_draw_raster_list(swr_context *c, int draw_mode, const void *vertices, size_t vertex_count, const int32_t *indices, size_t index_count)
+{
+    if (!c) return fail(-1, "null context");
+    if (index_count && (!indices || !vertices)) return fail(-1, "null vertices / indices");
+    if (index_count == 0) return 0;
+    return drawCommon(c, draw_mode, index_count, indices, vertices, vertex_count);
+}
+
+int swr_finish(swr_context *c)
+{
+    if (!c) return fail(-1, "null context");
+    if (int rc = setDevice(c)) return rc;
+    if (c->countersInit) {
+        Counters *dc = static_cast<Counters *>(c->counters.ptr);
+        CUDA_TRY(cudaMemcpyAsync(c->hostFlags, &dc->stickyFlag, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaMemsetAsync(&dc->stickyFlag, 0, sizeof(uint32_t), c->stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (c->hostFlags && c->hostFlags[0]) {
+        const uint32_t f = c->hostFlags[0];
+        c->hostFlags[0] = 0;
+        if (f & 1u) return fail(-30, "geometry scratch exhausted: the last draw produced nothing (raise swr_set_scratch_limit)");
+        if (f & 2u) return fail(-31, "a line longer than %d DDA steps was dropped", kMaxLineSteps);
+    }
+    return 0;
+}
+
+int swr_get_stats(swr_context *c, swr_stats *out)
+{
+    if (!c || !out) return fail(-1, "null argument");
+    if (int rc = setDevice(c)) return rc;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (c->counters.ptr) {
+        Counters h;
+        CUDA_TRY(cudaMemcpy(&h, c->counters.ptr, sizeof(h), cudaMemcpyDeviceToHost));
+        c->stats.fragments = h.fragments;
+    }
+    if (c->haveDrawEvents) {
+        cudaEventElapsedTime(&c->stats.last_geometry_ms, c->evGeom0, c->evGeom1);
+        cudaEventElapsedTime(&c->stats.last_tile_ms, c->evGeom1, c->evTile1);
+    }
+    c->stats.scratch_bytes = scratchBytes(c);
+    *out = c->stats;
+    return 0;
+}
+
+int swr_reset_stats(swr_context *c)
+{
+    if (!c) return fail(-1, "null context");
+    if (int rc = setDevice(c)) return rc;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (c->counters.ptr) CUDA_TRY(cudaMemset(&static_cast<Counters *>(c->counters.ptr)->fragments, 0, sizeof(unsigned long long)));
+    const uint64_t scratch = c->stats.scratch_bytes;
+    const int tile = c->stats.last_tile_size;
+    memset(&c->stats, 0, sizeof(c->stats));
+    c->stats.scratch_bytes = scratch;
+    c->stats.last_tile_size = tile;
+    return 0;
+}
+
+int swr_timer_begin(swr_context *c)
+{
+    if (!c) return fail(-1, "null context");
+    if (int rc = setDevice(c)) return rc;
+    CUDA_TRY(cudaEventRecord(c->evTimer0, c->stream));
+    return 0;
+}
+
+int swr_timer_end(swr_context *c, float *ms)
+{
+    if (!c || !ms) return fail(-1, "null argument");
+    if (int rc = setDevice(c)) return rc;
+    CUDA_TRY(cudaEventRecord(c->evTimer1, c->stream));
+    CUDA_TRY(cudaEventSynchronize(c->evTimer1));
+    CUDA_TRY(cudaEventElapsedTime(ms, c->evTimer0, c->evTimer1));
+    return 0;
+}
+
+void *swr_device_alloc(swr_context *c, size_t bytes)
+{
+    if (!c) return nullptr;
+    cudaSetDevice(c->device);
+    void *p = nullptr;
+    if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) {
+        fail(-101, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(cudaGetLastError()));
+        return nullptr;
+    }
+    return p;
+}
+
+int swr_device_free(swr_context *c, void *ptr)
+{
+    if (!c) return fail(-1, "null context");
+    if (int rc = setDevice(c)) return rc;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaFree(ptr));
+    return 0;
+}
+
+void *swr_host_alloc_pinned(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+        fail(-101, "cudaMallocHost(%zu) failed: %s", bytes, cudaGetErrorString(cudaGetLastError()));
+        return nullptr;
+    }
+    return p;
+}
+
+int swr_host_free_pinned(void *ptr)
+{
+    CUDA_TRY(cudaFreeHost(ptr));
+    return 0;
+}
+
+int swr_memcpy_h2d(swr_context *c, void *dst, const void *src, size_t bytes)
+{
+    if (!c) return fail(-1, "null context");
+    if (int rc = setDevice(c)) return rc;
+    CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+    return 0;
+}
+
+int swr_memcpy_d2h(swr_context *c, void *dst, const void *src, size_t bytes)
+{
+    if (!c) return fail(-1, "null context");
+    if (int rc = setDevice(c)) return rc;
+    CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+    return 0;
+}
+
+int swr_memset32(swr_context *c, void *dst, uint32_t value, size_t count)
+{
+    if (!c) return fail(-1, "null context");
+    if (int rc = setDevice(c)) return rc;
+    if (count == 0) return 0;
+    const int blocks = (int)std::min<size_t>((count + 1023) / 1024, 148 * 8);
+    fill32Kernel<<<blocks, 256, 0, c->stream>>>(static_cast<uint32_t *>(dst), value, count);
+    c->stats.kernel_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int swr_flush_l2(swr_context *c)
+{
+    if (!c) return fail(-1, "null context");
+    if (int rc = setDevice(c)) return rc;
+    const size_t bytes = (size_t)256 << 20;
+    if (int rc = c->l2flush.reserve(bytes)) return rc;
+    fill32Kernel<<<148 * 8, 256, 0, c->stream>>>(static_cast<uint32_t *>(c->l2flush.ptr), 0u, bytes / 4);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int64_t swr_owned_tile_count(int width, int height, int tile_size, int rank, int world)
+{
+    const int tilesX = (width + tile_size - 1) / tile_size, tilesY = (height + tile_size - 1) / tile_size;
+    int64_t n = 0;
+    for (int ty = 0; ty < tilesY; ++ty)
+        for (int tx = 0; tx < tilesX; ++tx) n += tileOwned(tx, ty, rank, world) ? 1 : 0;
+    return n;
+}
+
+static int exchangeTiles(swr_context *c, int slot, int rank, int world, int tile_size, void *buf, bool pack)
+{
+    if (!c) return fail(-1, "null context");
+    if (int rc = setDevice(c)) return rc;
+    if (slot < 0 || slot >= SWR_MAX_RENDER_TARGETS || !c->rt[slot].ptr) return fail(-2, "render target slot %d not registered", slot);
+    if (tile_size != 32 && tile_size != 64) return fail(-2, "tile size must be 32 or 64");
+    const int shift = tile_size == 64 ? 6 : 5;
+    const int tilesX = (c->rtW + tile_size - 1) / tile_size, tilesY = (c->rtH + tile_size - 1) / tile_size;
+    const int key[5] = { tile_size, rank, world, c->rtW, c->rtH };
+    if (memcmp(key, c->ownedKey, sizeof(key)) != 0 || !c->ownedIdx.ptr) {
+        std::vector<int> owned((size_t)tilesX * tilesY, -1);
+        int n = 0;
+        for (int t = 0; t < tilesX * tilesY; ++t)
+            if (tileOwned(t % tilesX, t / tilesX, rank, world)) owned[t] = n++;
+        if (int rc = c->ownedIdx.reserve(owned.size() * sizeof(int))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(c->ownedIdx.ptr, owned.data(), owned.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));   // `owned` is a temporary
+        memcpy(c->ownedKey, key, sizeof(key));
+    }
+    if (pack)
+        tileExchangeKernel<true><<<tilesX * tilesY, 256, 0, c->stream>>>((char *)c->rt[slot].ptr, c->rt[slot].pitch, c->rtW, c->rtH, shift,
+                                                                       tilesX, tilesY, rank, world, (const int *)c->ownedIdx.ptr, (uint32_t *)buf);
+    else
+        tileExchangeKernel<false><<<tilesX * tilesY, 256, 0, c->stream>>>((char *)c->rt[slot].ptr, c->rt[slot].pitch, c->rtW, c->rtH, shift,
+                                                                        tilesX, tilesY, rank, world, (const int *)c->ownedIdx.ptr, (uint32_t *)buf);
+    c->stats.kernel_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int swr_pack_tiles(swr_context *c, int slot, int rank, int world, int tile_size, void *dst_device)
+{
+    return exchangeTiles(c, slot, rank, world, tile_size, dst_device, true);
+}
+
+int swr_unpack_tiles(swr_context *c, int slot, int rank, int world, int tile_size, const void *src_device)
+{
+    return exchangeTiles(c, slot, rank, world, tile_size, const_cast<void *>(src_device), false);
+}
+
+int swr_debug_enable_stream(swr_context *c, int enable)
+{
+    if (!c) return fail(-1, "null context");
+    c->debugStream = enable != 0;
+    return 0;
+}
+
+// Records of the last pass in emission order (per batch: original slots, then fan extras).
+int64_t swr_debug_read_stream(swr_context *c, int16_t *bbox, uint32_t *ordinal, float *verts, int64_t cap)
+{
+    if (!c) return fail(-1, "null context");
+    if (int rc = setDevice(c)) return rc;
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) return fail(-100, "sync failed");
+    const int n = c->lastPassPrims;
+    if (n == 0 || !c->bbox.ptr) return 0;
+    const int batches = (n + kBatch - 1) / kBatch;
+    std::vector<uint2> extra(batches);
+    if (cudaMemcpy(extra.data(), c->extra.ptr, sizeof(uint2) * batches, cudaMemcpyDeviceToHost) != cudaSuccess) return fail(-100, "copy failed");
+    size_t maxRec = (size_t)batches * kBatch;
+    for (const uint2 &e : extra) maxRec = std::max(maxRec, (size_t)e.x + e.y);
+    std::vector<Box16> hb(maxRec);
+    std::vector<float> hv;
+    if (cudaMemcpy(hb.data(), c->bbox.ptr, sizeof(Box16) * maxRec, cudaMemcpyDeviceToHost) != cudaSuccess) return fail(-100, "copy failed");
+    if (verts && c->dbgVerts.ptr) {
+        hv.resize(maxRec * 12);
+        if (cudaMemcpy(hv.data(), c->dbgVerts.ptr, sizeof(float) * 12 * maxRec, cudaMemcpyDeviceToHost) != cudaSuccess) return fail(-100, "copy failed");
+    }
+    int64_t out = 0;
+    auto put = [&](size_t rec, uint32_t ord) {
+        if (out < cap) {
+            if (bbox) memcpy(bbox + out * 4, &hb[rec], 8);
+            if (ordinal) ordinal[out] = ord;
+            if (verts && !hv.empty()) memcpy(verts + out * 12, &hv[rec * 12], 48);
+        }
+        ++out;
+    };
+    for (int b = 0; b < batches; ++b) {
+        const int cnt = std::min(kBatch, n - b * kBatch);
+        const uint32_t ord0 = (c->lastFirstBatch + (uint32_t)b) * SWR_ORDINAL_STRIDE;
+        for (int s = 0; s < cnt; ++s) put((size_t)b * kBatch + s, ord0 + (uint32_t)s);
+        for (uint32_t e = 0; e < extra[b].y; ++e) put((size_t)extra[b].x + e, ord0 + (uint32_t)cnt + e);
+    }
+    return out;
+}
+
+} // extern "C"

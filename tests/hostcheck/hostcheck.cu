@@ -1,0 +1,274 @@
+// hostcheck.cu -- TEST INFRASTRUCTURE ONLY (never part of the product, never shipped).
+//
+// Runs the product's parity-critical DEVICE MATH on the host: the __host__ __device__ functions
+// of include/swr/detail/{geometry,tile}.cuh (clip, transform, cull, setup, footprint, coverage
+// masks, fragment chains) are called from a plain sequential loop that stands in for the two
+// kernels' thread / warp orchestration.  The result is diffed against the oracle by
+// tests/test_hostcheck.py without a GPU, so that a GPU run only has to prove the orchestration
+// (binning order, scans, shared-memory staging).  Built by nvcc as host code with
+// -Xcompiler -ffp-contract=off; no kernel is launched.
+#include <cuda_runtime.h>
+
+#include <cstring>
+#include <vector>
+
+#include <swr/VertexShaderBase.h>
+#include <swr/PixelShaderBase.h>
+#include <swr/detail/geometry.cuh>
+#include <swr/detail/tile.cuh>
+
+#include "../../oracle/swr_scene.h"
+
+using namespace swr;
+using namespace swr::detail;
+
+namespace {
+
+swr_scene *g_s = nullptr;
+
+struct PosColorVertex { float x, y, z, r, g, b; };
+struct ObjVertex { float px, py, pz, nx, ny, nz, u, v; };
+
+void mvpTransform(const float *m, float x, float y, float z, VertexShaderOutput *out)
+{
+    const float w = 1.0f;
+    out->x = m[0] * x + m[1] * y + m[2] * z + m[3] * w;
+    out->y = m[4] * x + m[5] * y + m[6] * z + m[7] * w;
+    out->z = m[8] * x + m[9] * y + m[10] * z + m[11] * w;
+    out->w = m[12] * x + m[13] * y + m[14] * z + m[15] * w;
+}
+
+template <int NP_>
+struct HostVS {
+    static const int AVarCount = 3;
+    static const int PVarCount = NP_;
+    static void processVertex(const void *in, VertexShaderOutput *out)
+    {
+        if (g_s->vs_kind == SWR_VS_POS_COLOR) {
+            const PosColorVertex *d = static_cast<const PosColorVertex *>(in);
+            out->x = d->x; out->y = d->y; out->z = d->z; out->w = 1.0f;
+            out->avar[0] = d->r; out->avar[1] = d->g; out->avar[2] = d->b;
+        } else if (g_s->vs_kind == SWR_VS_MVP_COLOR) {
+            const PosColorVertex *d = static_cast<const PosColorVertex *>(in);
+            mvpTransform(g_s->mvp, d->x, d->y, d->z, out);
+            out->avar[0] = d->r; out->avar[1] = d->g; out->avar[2] = d->b;
+        } else {
+            const ObjVertex *d = static_cast<const ObjVertex *>(in);
+            mvpTransform(g_s->mvp, d->px, d->py, d->pz, out);
+            out->avar[0] = d->nx; out->avar[1] = d->ny; out->avar[2] = d->nz;
+            out->pvar[0] = d->u; out->pvar[1] = d->v;
+        }
+    }
+};
+
+unsigned packRGB(const PixelData &p)
+{
+    int rint = (int)(p.avar[0] * 255);
+    int gint = (int)(p.avar[1] * 255);
+    int bint = (int)(p.avar[2] * 255);
+    return (unsigned)(rint << 16 | gint << 8 | bint);
+}
+
+struct HPSCountId : PixelShaderBase<HPSCountId> {
+    static void drawPixel(const PixelData &p)
+    {
+        g_s->fragments++;
+        int i = p.x + g_s->width * p.y;
+        g_s->count[i]++;
+        g_s->prim_id[i] = p.primitiveOrdinal;
+    }
+};
+struct HPSGouraud : PixelShaderBase<HPSGouraud> {
+    static const int AVarCount = 3;
+    static void drawPixel(const PixelData &p)
+    {
+        g_s->fragments++;
+        g_s->color[p.x + g_s->width * p.y] = packRGB(p);
+    }
+};
+struct HPSGouraudDepth : PixelShaderBase<HPSGouraudDepth> {
+    static const bool InterpolateZ = true;
+    static const int AVarCount = 3;
+    static void drawPixel(const PixelData &p)
+    {
+        g_s->fragments++;
+        int i = p.x + g_s->width * p.y;
+        if (p.z < g_s->depth[i]) { g_s->depth[i] = p.z; g_s->color[i] = packRGB(p); }
+    }
+};
+struct HPSVaryDump : PixelShaderBase<HPSVaryDump> {
+    static const bool InterpolateZ = true;
+    static const bool InterpolateW = true;
+    static const int AVarCount = 3;
+    static const int PVarCount = 2;
+    static void drawPixel(const PixelData &p)
+    {
+        g_s->fragments++;
+        size_t n = (size_t)g_s->width * g_s->height, i = (size_t)p.x + (size_t)g_s->width * p.y;
+        float *v = g_s->vary;
+        v[0 * n + i] = p.z; v[1 * n + i] = p.w; v[2 * n + i] = p.invw;
+        v[3 * n + i] = p.avar[0]; v[4 * n + i] = p.avar[1]; v[5 * n + i] = p.avar[2];
+        v[6 * n + i] = p.pvar[0]; v[7 * n + i] = p.pvar[1];
+        g_s->count[i]++;
+    }
+};
+
+template <class VS>
+void shadeHost(const swr_scene *s, int index, CVert<VS::AVarCount, VS::PVarCount> &o)
+{
+    VertexShaderOutput out;
+    VS::processVertex((const char *)s->vertices + (size_t)s->stride * (size_t)index, &out);
+    o.x = out.x; o.y = out.y; o.z = out.z; o.w = out.w;
+    for (int i = 0; i < VS::AVarCount; ++i) o.a[i] = out.avar[i];
+    for (int i = 0; i < VS::PVarCount; ++i) o.p[i] = out.pvar[i];
+}
+
+struct Store {
+    std::vector<Box16> bbox;
+    std::vector<float4> head, span;
+    std::vector<float> params;
+    std::vector<uint32_t> order;     // record ids in emission order
+};
+
+template <class VS, class PS>
+int run(swr_scene *s)
+{
+    constexpr int NA = VS::AVarCount, NP = VS::PVarCount;
+    typedef CVert<NA, NP> V;
+    typedef PsTraits<PS> TR;
+    const int per = s->draw_mode + 1;
+    const int64_t nprim = s->index_count / per;
+
+    GeomArgs g;
+    memset(&g, 0, sizeof(g));
+    g.drawMode = s->draw_mode;
+    g.px = s->vp_w / 2.0f; g.py = s->vp_h / 2.0f;
+    g.ox = (s->vp_x + g.px); g.oy = (s->vp_y + g.py);
+    g.depthN = s->depth_n; g.depthF = s->depth_f;
+    g.cullMode = s->cull_mode; g.rasterMode = s->raster_mode;
+    g.scMinX = s->sc_x; g.scMinY = s->sc_y; g.scMaxX = s->sc_x + s->sc_w; g.scMaxY = s->sc_y + s->sc_h;
+    g.nA = TR::NA; g.nP = TR::NP; g.useZ = TR::Z; g.useW = TR::W;
+    g.paramStride = paramFloats(s->draw_mode, g.nA, g.nP, g.useZ, g.useW);
+    uint32_t errorFlags[2] = { 0, 0 };
+    g.errorFlag = errorFlags;
+
+    const size_t cap = (size_t)nprim * (s->draw_mode == 2 ? kMaxFan : 1) + 1;
+    Store st;
+    st.bbox.assign(cap, deadBox());
+    st.head.resize(cap * 3);
+    st.span.resize(cap * 3);
+    st.params.resize(cap * (size_t)g.paramStride + 4);
+    g.bbox = st.bbox.data(); g.head = st.head.data(); g.span = st.span.data(); g.params = st.params.data();
+
+    // ---- geometry stage, in emission order: per batch the original slots, then the fan extras
+    uint32_t nextRec = 0;
+    for (int64_t base = 0, batch = 0; base < nprim; base += kBatch, ++batch) {
+        const int cnt = (int)std::min<int64_t>(kBatch, nprim - base);
+        const uint32_t ord0 = (uint32_t)batch * SWR_ORDINAL_STRIDE;
+        std::vector<uint32_t> extras;
+        uint32_t slotExtra = (uint32_t)cnt;
+        for (int i = 0; i < cnt; ++i) {
+            const int32_t *ip = s->indices + (base + i) * per;
+            const uint32_t rec = nextRec++;
+            Box16 box = deadBox();
+            if (s->draw_mode == 2) {
+                V a[kMaxPoly], b[kMaxPoly], *poly = a;
+                shadeHost<VS>(s, ip[0], a[0]); shadeHost<VS>(s, ip[1], a[1]); shadeHost<VS>(s, ip[2], a[2]);
+                const int mask = outcode(a[0].x, a[0].y, a[0].z, a[0].w) | outcode(a[1].x, a[1].y, a[1].z, a[1].w) |
+                                 outcode(a[2].x, a[2].y, a[2].z, a[2].w);
+                int n = 3;
+                if (mask) n = clipTriangle<NA, NP>(a, b, mask, &poly);
+                if (n >= 3) {
+                    box = emitClipTriangle<NA, NP>(g, rec, ord0 + (uint32_t)i, poly[0], poly[1], poly[2]);
+                    for (int k = 1; k + 2 < n; ++k) {
+                        const uint32_t er = nextRec++;
+                        st.bbox[er] = emitClipTriangle<NA, NP>(g, er, ord0 + slotExtra++, poly[0], poly[k + 1], poly[k + 2]);
+                        extras.push_back(er);
+                    }
+                }
+            } else if (s->draw_mode == 1) {
+                V c0, c1;
+                shadeHost<VS>(s, ip[0], c0); shadeHost<VS>(s, ip[1], c1);
+                box = emitClipLine<NA, NP>(g, rec, ord0 + (uint32_t)i, c0, c1);
+            } else {
+                V c0;
+                shadeHost<VS>(s, ip[0], c0);
+                if (outcode(c0.x, c0.y, c0.z, c0.w) == 0) {
+                    toScreen(g, c0);
+                    box = emitScreenPoint<NA, NP>(g, rec, ord0 + (uint32_t)i, c0);
+                }
+            }
+            st.bbox[rec] = box;
+            st.order.push_back(rec);
+        }
+        st.order.insert(st.order.end(), extras.begin(), extras.end());
+    }
+
+    // ---- raster stage: every record in emission order, every 8x8 block of its footprint
+    TileArgs t;
+    memset(&t, 0, sizeof(t));
+    t.bbox = g.bbox; t.head = g.head; t.params = g.params; t.span = g.span; t.paramStride = g.paramStride;
+    t.rtWidth = s->width; t.rtHeight = s->height;
+    t.scMinX = g.scMinX; t.scMinY = g.scMinY; t.scMaxX = g.scMaxX; t.scMaxY = g.scMaxY;
+    PixelData p;
+    memset(&p, 0, sizeof(p));
+    for (uint32_t rec : st.order) {
+        const Box16 bb = st.bbox[rec];
+        if (bb.x0 > bb.x1) continue;
+        s->primitives_out++;
+        for (int gy = bb.y0 & ~7; gy <= bb.y1; gy += 8) {
+            for (int gx = bb.x0 & ~7; gx <= bb.x1; gx += 8) {
+                uint64_t m;
+                const float4 h0 = t.head[(size_t)rec * 3], h1 = t.head[(size_t)rec * 3 + 1], h2 = t.head[(size_t)rec * 3 + 2];
+                if (s->draw_mode == 2) {
+                    if (f2u(h2.y) & kModeSpan) m = coverSpan(t.span[(size_t)rec * 3], t.span[(size_t)rec * 3 + 1], t.span[(size_t)rec * 3 + 2], gx, gy, t.scMinX, t.scMaxX);
+                    else m = coverBlock(h0, h1, h2, gx, gy);
+                } else if (s->draw_mode == 1) {
+                    m = coverLine(h0, h1, gx, gy, t);
+                } else {
+                    const int lx = f2i(h0.x) - gx, ly = f2i(h0.y) - gy;
+                    m = ((unsigned)lx < 8u && (unsigned)ly < 8u) ? 1ull << (ly * 8 + lx) : 0ull;
+                }
+                for (int bit = 0; bit < 64; ++bit) {
+                    if (!((m >> bit) & 1)) continue;
+                    const int xx = bit & 7, yy = bit >> 3;
+                    if (gx + xx >= s->width || gy + yy >= s->height) continue;
+                    if (s->draw_mode == 2) shadeTriangleFragment<PS>(t, rec, gx, gy, xx, yy, p);
+                    else if (s->draw_mode == 1) shadeLineFragments<PS>(t, rec, gx + xx, gy + yy, p);
+                    else shadePointFragment<PS>(t, rec, gx + xx, gy + yy, p);
+                }
+            }
+        }
+    }
+    return (int)errorFlags[1];
+}
+
+template <class PS>
+int runVS(swr_scene *s)
+{
+    if (s->vs_kind == SWR_VS_MVP_NORMAL_UV) return run<HostVS<2>, PS>(s);
+    if (PS::PVarCount > 0) return -3;
+    return run<HostVS<0>, PS>(s);
+}
+
+} // namespace
+
+// Note: unlike the oracle, primitives_out counts records with a live footprint (the tile kernel's
+// notion), and within one primitive the fragment order is block-major -- neither is observable in
+// the per-pixel results the test compares.
+extern "C" int hostcheck_draw(swr_scene *s)
+{
+    g_s = s;
+    s->fragments = 0;
+    s->primitives_out = 0;
+    s->stream_len = 0;
+    switch (s->ps_kind) {
+    case SWR_PS_COUNT_ID: return runVS<HPSCountId>(s);
+    case SWR_PS_GOURAUD: return runVS<HPSGouraud>(s);
+    case SWR_PS_GOURAUD_DEPTH: return runVS<HPSGouraudDepth>(s);
+    case SWR_PS_VARY_DUMP: return runVS<HPSVaryDump>(s);
+    default: return -2;
+    }
+}
+
+extern "C" int hostcheck_draw_raster_triangles(swr_scene *, const float *, int64_t) { return -1; }

@@ -1,0 +1,149 @@
+"""GPU: the CUDA path, called through the C ABI, against the oracle on the same seeded inputs --
+bit-exact for every output buffer (coverage counts, last-writer ordinals, depth, colour, and the
+interpolated z / w / 1/w / varyings: tolerance 0 ULP, the tile kernel replays the reference's
+fp32 add chains)."""
+import numpy as np
+import pytest
+
+import common
+from softwarerenderer_b200 import scenes as S
+
+pytestmark = pytest.mark.gpu
+
+SCENES = common.parity_scenes()
+
+
+@pytest.fixture(scope="module")
+def renderers():
+    from softwarerenderer_b200.api import SceneRenderer
+    cache = {}
+
+    def get(w, h, tile=0):
+        key = (w, h, tile)
+        if key not in cache:
+            cache[key] = SceneRenderer(w, h, tile_size=tile)
+        return cache[key]
+    yield get
+    for r in cache.values():
+        r.close()
+
+
+def check(got, want, label):
+    bad = common.diff_buffers(got, want)
+    assert got["fragments"] == want["fragments"], f"{label}: {got['fragments']} fragments, oracle {want['fragments']}"
+    assert not bad, f"{label}: buffers differ from the oracle (words): {bad}"
+
+
+@pytest.mark.parametrize("label,scene", SCENES, ids=[l for l, _ in SCENES])
+def test_gpu_matches_oracle(oracle, renderers, label, scene):
+    got = renderers(scene.width, scene.height).render(scene)
+    check(got, oracle.run(scene, "oracle"), label)
+
+
+@pytest.mark.parametrize("tile", [32, 64])
+def test_tile_size_independence(oracle, renderers, tile):
+    for scene in (S.config_c3(250, 200, 480, 270, ps=S.PS_COUNT_ID), S.config_c0(ntri=1500, ps=S.PS_COUNT_ID, raster_mode=S.RASTER_BLOCK)):
+        got = renderers(scene.width, scene.height, tile).render(scene)
+        check(got, oracle.run(scene, "oracle"), f"{scene.name}_tile{tile}")
+
+
+def test_gpu_matches_reference_golden(renderers):
+    """Directly against the reference's golden vectors (no oracle in the loop)."""
+    import zlib
+    ka = common.known_answers()
+    for label, scene in SCENES[::5]:
+        got = renderers(scene.width, scene.height).render(scene)
+        assert got["fragments"] == ka[label]["fragments"], label
+        for k in common.BUFFERS:
+            assert (zlib.crc32(got[k].view(np.uint8).tobytes()) & 0xFFFFFFFF) == ka[label]["crc_" + k], f"{label}:{k}"
+
+
+def test_benchmark_full_known_answers(renderers):
+    """Benchmark.cpp's workload at full size: fragment counts of SURVEY.md section 4."""
+    full = S.config_c0(ps=S.PS_COUNT_ID)
+    r = renderers(640, 480)
+    ka = common.known_answers()
+    for name, mode, frags in (("span", 0, 240235639), ("block", 1, 240235776), ("adaptive", 2, 240235758)):
+        got = r.render(full.replace(raster_mode=mode))
+        assert got["fragments"] == frags, name
+        assert int((got["count"] > 0).sum()) == ka[f"benchmark_full_{name}"]["covered"]
+        import zlib
+        for k in ("count", "prim_id"):
+            assert (zlib.crc32(got[k].view(np.uint8).tobytes()) & 0xFFFFFFFF) == ka[f"benchmark_full_{name}"]["crc_" + k], f"{name}:{k}"
+
+
+def test_empty_and_ragged_counts(oracle, renderers):
+    base = S.config_c0(ps=S.PS_COUNT_ID, ntri=1025)
+    r = renderers(640, 480)
+    got = r.render(base.replace(indices=base.indices[:0]))
+    assert got["fragments"] == 0 and int(got["count"].sum()) == 0
+    for n in (1, 1023, 1024, 1025):
+        sc = base.replace(indices=base.indices[:3 * n])
+        check(r.render(sc), oracle.run(sc, "oracle"), f"ragged_{n}")
+
+
+def test_split_draw_equals_single_draw(renderers):
+    """Draw order across draw calls: two draws split at a batch boundary == one draw."""
+    scene = S.config_c0(ps=S.PS_GOURAUD_DEPTH, ntri=4096, raster_mode=S.RASTER_BLOCK)
+    r = renderers(640, 480)
+    one = r.render(scene)
+    r.targets.clear()
+    r.draw(scene.replace(indices=scene.indices[:3 * 2048]))
+    r.draw(scene.replace(indices=scene.indices[3 * 2048:]))
+    two = r.targets.download()
+    assert not common.diff_buffers(one, two, ("color", "depth"))
+
+
+def test_multi_pass_equals_single_pass(oracle, renderers):
+    """A tiny scratch limit forces several passes per draw; results must not change."""
+    from softwarerenderer_b200.api import SceneRenderer
+    scene = S.config_c3(250, 200, 480, 270, ps=S.PS_COUNT_ID)
+    sr = SceneRenderer(scene.width, scene.height)
+    sr.r.setScratchLimit(64 << 20)
+    got = sr.render(scene)
+    assert got["stats"].passes > 1
+    check(got, oracle.run(scene, "oracle"), "multipass")
+    sr.close()
+
+
+def test_device_resident_inputs(oracle, renderers):
+    """Vertex / index buffers already in HBM are used in place."""
+    scene = S.config_c2(100, 50, 480, 270)
+    sr = renderers(scene.width, scene.height)
+    vb = sr.r.alloc(scene.vertices.nbytes)
+    ib = sr.r.alloc(scene.indices.nbytes)
+    sr.r.upload(vb, scene.vertices)
+    sr.r.upload(ib, scene.indices)
+    sr.targets.clear()
+    sr.r.resetStats()
+    sr.draw(scene, vertices=vb, indices=ib)
+    got = sr.targets.download()
+    got["fragments"] = int(sr.r.stats().fragments)
+    check(got, oracle.run(scene, "oracle"), "resident")
+    sr.r.free(vb)
+    sr.r.free(ib)
+
+
+def test_tile_partition_union_equals_full(oracle, renderers):
+    """Sort-first: ranks render disjoint tile sets; their union is the full image."""
+    from softwarerenderer_b200.api import SceneRenderer
+    scene = S.config_c0(ntri=1500, ps=S.PS_COUNT_ID, raster_mode=S.RASTER_BLOCK)
+    want = oracle.run(scene, "oracle")
+    world = 4
+    acc = None
+    frags = 0
+    for rank in range(world):
+        sr = SceneRenderer(scene.width, scene.height)
+        sr.r.setTilePartition(rank, world)
+        got = sr.render(scene)
+        frags += got["fragments"]
+        if acc is None:
+            acc = {k: got[k].copy() for k in common.BUFFERS}
+        else:
+            touched = got["count"] > 0
+            assert not np.any(touched & (acc["count"] > 0)), "two ranks rendered the same pixel"
+            for k in ("count", "prim_id", "color", "depth"):
+                acc[k][touched] = got[k][touched]
+        sr.close()
+    assert frags == want["fragments"]
+    assert not common.diff_buffers(acc, want, ("count", "prim_id"))

@@ -12,7 +12,9 @@ namespace swr {
 namespace detail {
 static __constant__ unsigned char g_uniformBlock[SWR_MAX_UNIFORM_BYTES];
 
-inline int uploadUniforms(const void *data, size_t bytes, void *stream)
+// static: every translation unit must get its OWN copy bound to its own g_uniformBlock (an inline
+// function would be merged across TUs by the linker and write a single block).
+static int uploadUniforms(const void *data, size_t bytes, void *stream)
 {
     if (bytes > SWR_MAX_UNIFORM_BYTES) return -1;
     return cudaMemcpyToSymbolAsync(g_uniformBlock, data, bytes, 0, cudaMemcpyHostToDevice, (cudaStream_t)stream) == cudaSuccess ? 0 : -2;

@@ -58,7 +58,7 @@ struct TileSmem {
     static constexpr size_t bytes = offCtl + 64;
 };
 
-struct Ctl { uint32_t accQ, accItems; };
+struct Ctl { uint32_t accQ, accItems; int nextBlock; };
 
 // Exclusive block scan of a packed (hi: count, lo: sum) pair.  Two barriers; scratch is double
 // buffered so back-to-back calls need no trailing barrier.
@@ -96,23 +96,41 @@ SWR_D bool boxOverlaps(const Box16 b, int X0, int Y0, int X1, int Y1)
     return b.x0 <= b.x1 && b.x0 <= X1 && b.x1 >= X0 && b.y0 <= Y1 && b.y1 >= Y0;
 }
 
-// position of the n-th (0-based) set bit of a 64-bit mask
+// position of the n-th (0-based) set bit: popcount binary search (the __fns intrinsic is a slow loop)
+SWR_D int nthSetBit32(uint32_t w, int n)
+{
+    int base = 0, c;
+    c = __popc(w & 0xffffu); if (n >= c) { n -= c; w >>= 16; base = 16; }
+    c = __popc(w & 0xffu);   if (n >= c) { n -= c; w >>= 8;  base += 8; }
+    c = __popc(w & 0xfu);    if (n >= c) { n -= c; w >>= 4;  base += 4; }
+    c = __popc(w & 0x3u);    if (n >= c) { n -= c; w >>= 2;  base += 2; }
+    c = (int)(w & 1u);       if (n >= c) base += 1;
+    return base;
+}
 SWR_D int nthSetBit64(uint64_t m, int n)
 {
     const uint32_t lo = (uint32_t)m, hi = (uint32_t)(m >> 32);
     const int cl = __popc(lo);
-    return n < cl ? (int)__fns(lo, 0, n + 1) : 32 + (int)__fns(hi, 0, n - cl + 1);
+    return n < cl ? nthSetBit32(lo, n) : 32 + nthSetBit32(hi, n - cl);
 }
-
-SWR_HD bool edgeIn(float v, bool tie) { return v > 0 || (v == 0 && tie); }   // EdgeEquation.h:58-61
 
 // ---- coverage of one 8x8 block ------------------------------------------------------------------
 // Block mode: Rasterizer.h:257-305 + PixelShaderBase.h:55-94.  (gx, gy) = block origin.
+//
+// Inside test (EdgeEquation.h:58-61)  v > 0 || (v == 0 && tie)  as ONE compare:  v > thr  with
+// thr = 0 for tie == false and thr = -denorm_min for tie == true (no float lies between the two,
+// -0 == 0, NaN fails both forms).
+//
+// Row skipping is exact, not conservative-approximate: along a row the reference's value chain
+// v, v+a, (v+a)+a, ... is monotone (an fp32 add of a constant is monotone), so its maximum is the
+// first value when a <= 0 and the last one when a > 0; if that maximum fails an edge's test no
+// pixel of the row can pass, and the 8 x 3 per-pixel tests are skipped.
 SWR_HD uint64_t coverBlock(const float4 h0, const float4 h1, const float4 h2, int gx, int gy)
 {
     const float ea[3] = { h0.x, h0.w, h1.z }, eb[3] = { h0.y, h1.x, h1.w }, ec[3] = { h0.z, h1.y, h2.x };
     const uint32_t flags = f2u(h2.y);
-    const bool tie[3] = { (flags & kTie0) != 0, (flags & kTie1) != 0, (flags & kTie2) != 0 };
+    const float negTiny = u2f(0x80000001u);
+    const float thr[3] = { (flags & kTie0) ? negTiny : 0.0f, (flags & kTie1) ? negTiny : 0.0f, (flags & kTie2) ? negTiny : 0.0f };
     const float xf = fadd(i2f(gx), 0.5f), yf = fadd(i2f(gy), 0.5f);
     const float s = 7.0f;
     float e00[3];
@@ -123,8 +141,8 @@ SWR_HD uint64_t coverBlock(const float4 h0, const float4 h1, const float4 h2, in
         const float e01 = fadd(e00[k], fmul(eb[k], s));                    // stepY(s)
         const float e10 = fadd(e00[k], fmul(ea[k], s));                    // stepX(s)
         const float e11 = fadd(e01, fmul(ea[k], s));
-        in[0][k] = edgeIn(e00[k], tie[k]); in[1][k] = edgeIn(e01, tie[k]);
-        in[2][k] = edgeIn(e10, tie[k]); in[3][k] = edgeIn(e11, tie[k]);
+        in[0][k] = e00[k] > thr[k]; in[1][k] = e01 > thr[k];
+        in[2][k] = e10 > thr[k]; in[3][k] = e11 > thr[k];
     }
     int all = 0;
     bool same = true;
@@ -137,13 +155,24 @@ SWR_HD uint64_t coverBlock(const float4 h0, const float4 h1, const float4 h2, in
     if (all == 0 && same) return 0ull;                                     // "special case": block skipped
     uint64_t mask = 0;
     float r0 = e00[0], r1 = e00[1], r2 = e00[2];
-#pragma unroll
+#pragma unroll 1
     for (int yy = 0; yy < 8; ++yy) {
-        float v0 = r0, v1 = r1, v2 = r2;
+        // last value of each edge's chain in this row (7 adds, the same ones the per-pixel walk does)
+        float l0 = r0, l1 = r1, l2 = r2;
 #pragma unroll
-        for (int xx = 0; xx < 8; ++xx) {
-            if (edgeIn(v0, tie[0]) && edgeIn(v1, tie[1]) && edgeIn(v2, tie[2])) mask |= 1ull << (yy * 8 + xx);
-            v0 = fadd(v0, ea[0]); v1 = fadd(v1, ea[1]); v2 = fadd(v2, ea[2]);
+        for (int xx = 0; xx < 7; ++xx) { l0 = fadd(l0, ea[0]); l1 = fadd(l1, ea[1]); l2 = fadd(l2, ea[2]); }
+        const bool dead = (ea[0] <= 0 && !(r0 > thr[0])) || (ea[0] > 0 && !(l0 > thr[0])) ||
+                          (ea[1] <= 0 && !(r1 > thr[1])) || (ea[1] > 0 && !(l1 > thr[1])) ||
+                          (ea[2] <= 0 && !(r2 > thr[2])) || (ea[2] > 0 && !(l2 > thr[2]));
+        if (!dead) {
+            float v0 = r0, v1 = r1, v2 = r2;
+            uint32_t rowMask = 0;
+#pragma unroll
+            for (int xx = 0; xx < 8; ++xx) {
+                if (v0 > thr[0] && v1 > thr[1] && v2 > thr[2]) rowMask |= 1u << xx;
+                v0 = fadd(v0, ea[0]); v1 = fadd(v1, ea[1]); v2 = fadd(v2, ea[2]);
+            }
+            mask |= (uint64_t)rowMask << (yy * 8);
         }
         r0 = fadd(r0, eb[0]); r1 = fadd(r1, eb[1]); r2 = fadd(r2, eb[2]);
     }
@@ -392,7 +421,7 @@ SWR_D void moveTile(const TileArgs &t, char *rtSmem, int X0, int Y0)
 
 // ---- the kernel -----------------------------------------------------------------------------------
 template <class PS, int MODE, int TLOG>
-__global__ void __launch_bounds__(kTileThreads, 2) tileKernel(const TileArgs t)
+__global__ void __launch_bounds__(kTileThreads, 3) tileKernel(const TileArgs t)
 {
     typedef PsTraits<PS> TR;
     typedef TileSmem<TLOG, TR::NRT> SM;
@@ -425,7 +454,7 @@ __global__ void __launch_bounds__(kTileThreads, 2) tileKernel(const TileArgs t)
     // ---- flush: coverage (A) + shading (B) of the queued primitives -----------------------------
     auto flushQueue = [&]() {
         if (nQ == 0) return;
-        if (tid == 0) qItem[nQ] = nItems;
+        if (tid == 0) { qItem[nQ] = nItems; ctl->nextBlock = 0; }
         for (int i = tid; i < NB * QW; i += kTileThreads) sBlockmap[i] = 0;
         if (!loaded) {
             moveTile<TLOG, TR::NRT, false>(t, rtSmem, X0, Y0);
@@ -470,7 +499,13 @@ __global__ void __launch_bounds__(kTileThreads, 2) tileKernel(const TileArgs t)
         PixelData p;
         p.rtBase = rtSmem;
         p.rtSlotStride = T * T * 4;
-        for (int b = wid; b < NB; b += kTileWarps) {
+        // a block belongs to ONE warp for the whole flush (per-pixel order); which warp takes which
+        // block is dynamic so that heavy blocks do not pile up on one warp
+        while (true) {
+            int b = 0;
+            if (lane == 0) b = atomicAdd(&ctl->nextBlock, 1);
+            b = __shfl_sync(0xffffffffu, b, 0);
+            if (b >= NB) break;
             const int bx = b % BPR, by = b / BPR;
             const int gx = X0 + bx * 8, gy = Y0 + by * 8;
             const uint32_t bm = lane < QW ? sBlockmap[b * QW + lane] : 0u;
@@ -498,7 +533,7 @@ __global__ void __launch_bounds__(kTileThreads, 2) tileKernel(const TileArgs t)
                 uint32_t q = 0, rec = 0;
                 uint64_t m = 0;
                 if (ivalid) {
-                    q = (uint32_t)wl * 32u + __fns(wbm, 0, (int)(j - wbase) + 1);
+                    q = (uint32_t)wl * 32u + (uint32_t)nthSetBit32(wbm, (int)(j - wbase));
                     rec = qRec[q];
                     const uint32_t rg = qRange[q];
                     const int bx0 = rg & 0xff, by0 = (rg >> 8) & 0xff, nx = (int)((rg >> 16) & 0xff) - bx0 + 1;

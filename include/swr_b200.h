@@ -121,6 +121,9 @@ SWR_API int swr_set_uniforms(swr_context *ctx, const void *data, size_t bytes);
 SWR_API int swr_set_tile_size(swr_context *ctx, int tile_size);
 SWR_API int swr_set_tile_partition(swr_context *ctx, int rank, int world);
 SWR_API int swr_set_scratch_limit(swr_context *ctx, size_t bytes);
+/* Enqueue on a caller-owned CUDA stream (a cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream)
+ * instead of the context's own; NULL restores the context's stream.  Waits for pending work first. */
+SWR_API int swr_set_stream(swr_context *ctx, void *cuda_stream);
 
 /* ---- draws ---------------------------------------------------------------------------------- */
 /* VertexProcessor::drawElements(mode, count, indices) (VertexProcessor.cpp:78-120).  `indices`

@@ -128,6 +128,10 @@ class Rasterizer:
     def setScratchLimit(self, nbytes: int):
         _lib.check(lib.swr_set_scratch_limit(self._ctx, nbytes), "setScratchLimit")
 
+    def setStream(self, cuda_stream: int):
+        """Enqueue on a caller-owned CUDA stream (e.g. torch.cuda.current_stream().cuda_stream); 0 = own stream."""
+        _lib.check(lib.swr_set_stream(self._ctx, cuda_stream or None), "setStream")
+
     def finish(self):
         _lib.check(lib.swr_finish(self._ctx), "finish")
 

@@ -96,7 +96,8 @@ bool isDevicePointer(const void *p)
 
 struct swr_context {
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;      // the stream draws are enqueued on
+    cudaStream_t ownStream = nullptr;   // created by swr_create
     cudaEvent_t evGeom0 = nullptr, evGeom1 = nullptr, evTile1 = nullptr, evTimer0 = nullptr, evTimer1 = nullptr;
     bool haveDrawEvents = false;
 
@@ -453,7 +454,8 @@ int swr_create(swr_context **out, int cuda_device)
     swr_context *c = new swr_context();
     c->device = cuda_device;
     cudaError_t e = cudaSetDevice(cuda_device);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->ownStream, cudaStreamNonBlocking);
+    c->stream = c->ownStream;
     cudaEvent_t *evs[] = { &c->evGeom0, &c->evGeom1, &c->evTile1, &c->evTimer0, &c->evTimer1 };
     for (cudaEvent_t *ev : evs)
         if (e == cudaSuccess) e = cudaEventCreate(ev);
@@ -483,7 +485,7 @@ void swr_destroy(swr_context *c)
     cudaEvent_t evs[] = { c->evGeom0, c->evGeom1, c->evTile1, c->evTimer0, c->evTimer1 };
     for (cudaEvent_t ev : evs)
         if (ev) cudaEventDestroy(ev);
-    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->ownStream) cudaStreamDestroy(c->ownStream);
     delete c;
 }
 
@@ -596,10 +598,19 @@ int swr_set_tile_partition(swr_context *c, int rank, int world)
     return 0;
 }
 
+int swr_set_stream(swr_context *c, void *cuda_stream)
+{
+    if (!c) return fail(-1, "null context");
+    if (int rc = setDevice(c)) return rc;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->ownStream;
+    return 0;
+}
+
 int swr_set_scratch_limit(swr_context *c, size_t bytes)
 {
     if (!c) return fail(-1, "null context");
-    c->scratchLimit = std::max<size_t>(bytes, (size_t)64 << 20);
+    c->scratchLimit = std::max<size_t>(bytes, (size_t)1 << 20);
     return 0;
 }
 
@@ -781,23 +792,28 @@ static int exchangeTiles(swr_context *c, int slot, int rank, int world, int tile
     if (tile_size != 32 && tile_size != 64) return fail(-2, "tile size must be 32 or 64");
     const int shift = tile_size == 64 ? 6 : 5;
     const int tilesX = (c->rtW + tile_size - 1) / tile_size, tilesY = (c->rtH + tile_size - 1) / tile_size;
-    const int key[5] = { tile_size, rank, world, c->rtW, c->rtH };
+    // ownedIdx[r][tile] = position of `tile` in rank r's exchange buffer; built once per geometry
+    const int ntiles = tilesX * tilesY;
+    const int key[5] = { tile_size, 0, world, c->rtW, c->rtH };
     if (memcmp(key, c->ownedKey, sizeof(key)) != 0 || !c->ownedIdx.ptr) {
-        std::vector<int> owned((size_t)tilesX * tilesY, -1);
-        int n = 0;
-        for (int t = 0; t < tilesX * tilesY; ++t)
-            if (tileOwned(t % tilesX, t / tilesX, rank, world)) owned[t] = n++;
+        std::vector<int> owned((size_t)world * ntiles, -1);
+        for (int r = 0; r < world; ++r) {
+            int n = 0;
+            for (int t = 0; t < ntiles; ++t)
+                if (tileOwned(t % tilesX, t / tilesX, r, world)) owned[(size_t)r * ntiles + t] = n++;
+        }
         if (int rc = c->ownedIdx.reserve(owned.size() * sizeof(int))) return rc;
         CUDA_TRY(cudaMemcpyAsync(c->ownedIdx.ptr, owned.data(), owned.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));   // `owned` is a temporary
         memcpy(c->ownedKey, key, sizeof(key));
     }
+    const int *ownedIndex = (const int *)c->ownedIdx.ptr + (size_t)rank * ntiles;
     if (pack)
         tileExchangeKernel<true><<<tilesX * tilesY, 256, 0, c->stream>>>((char *)c->rt[slot].ptr, c->rt[slot].pitch, c->rtW, c->rtH, shift,
-                                                                       tilesX, tilesY, rank, world, (const int *)c->ownedIdx.ptr, (uint32_t *)buf);
+                                                                       tilesX, tilesY, rank, world, ownedIndex, (uint32_t *)buf);
     else
         tileExchangeKernel<false><<<tilesX * tilesY, 256, 0, c->stream>>>((char *)c->rt[slot].ptr, c->rt[slot].pitch, c->rtW, c->rtH, shift,
-                                                                        tilesX, tilesY, rank, world, (const int *)c->ownedIdx.ptr, (uint32_t *)buf);
+                                                                        tilesX, tilesY, rank, world, ownedIndex, (uint32_t *)buf);
     c->stats.kernel_launches++;
     CUDA_TRY(cudaGetLastError());
     return 0;

@@ -1,0 +1,94 @@
+"""Sort-first multi-GPU partition and framebuffer composite (K7 of SURVEY.md 2.3 / 8(e)).
+
+Geometry is replicated; screen tiles are interleaved across ranks with
+    owner(tx, ty) = (tx + 3 * ty) % world           (include/swr/detail/common.h: tileOwned)
+Each rank rasterizes only its tiles.  The one exchange step per frame is a pure copy of disjoint
+tiles (no reduction, so bit-exactness is preserved): every rank packs its tiles into a dense
+tile-major buffer, one NCCL all-gather moves them over NVLink, every rank unpacks its peers'
+tiles into its own surface and ends up with the full image.
+
+The layout helpers are plain numpy (host logic, covered by world_size-2 gloo tests on CPU); on
+the GPU the pack / unpack are CUDA kernels behind swr_pack_tiles / swr_unpack_tiles.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def tile_grid(width: int, height: int, tile: int):
+    return (width + tile - 1) // tile, (height + tile - 1) // tile
+
+
+def tile_owner(tx, ty, world: int):
+    return (tx + 3 * ty) % world if world > 1 else 0 * (tx + ty)
+
+
+def owned_tiles(width: int, height: int, tile: int, rank: int, world: int) -> np.ndarray:
+    """Tile ids (ty * tiles_x + tx) owned by `rank`, ascending -- the order of the exchange buffer."""
+    tiles_x, tiles_y = tile_grid(width, height, tile)
+    ty, tx = np.divmod(np.arange(tiles_x * tiles_y), tiles_x)
+    return np.nonzero(tile_owner(tx, ty, world) == rank)[0]
+
+
+def max_owned(width: int, height: int, tile: int, world: int) -> int:
+    return max(len(owned_tiles(width, height, tile, r, world)) for r in range(world))
+
+
+def pack_tiles_host(surface: np.ndarray, tile: int, rank: int, world: int, slots: int = 0) -> np.ndarray:
+    """surface [H, W] 32-bit -> [n_owned (or slots), tile, tile]; pixels outside the surface are 0."""
+    h, w = surface.shape
+    tiles_x, _ = tile_grid(w, h, tile)
+    ids = owned_tiles(w, h, tile, rank, world)
+    out = np.zeros((max(slots, len(ids)), tile, tile), dtype=surface.dtype)
+    for k, t in enumerate(ids):
+        ty, tx = divmod(int(t), tiles_x)
+        blk = surface[ty * tile:(ty + 1) * tile, tx * tile:(tx + 1) * tile]
+        out[k, :blk.shape[0], :blk.shape[1]] = blk
+    return out
+
+
+def unpack_tiles_host(surface: np.ndarray, buf: np.ndarray, tile: int, rank: int, world: int) -> None:
+    """Inverse of pack_tiles_host: writes rank's tiles from `buf` into `surface` in place."""
+    h, w = surface.shape
+    tiles_x, _ = tile_grid(w, h, tile)
+    for k, t in enumerate(owned_tiles(w, h, tile, rank, world)):
+        ty, tx = divmod(int(t), tiles_x)
+        blk = surface[ty * tile:(ty + 1) * tile, tx * tile:(tx + 1) * tile]
+        blk[...] = buf[k, :blk.shape[0], :blk.shape[1]]
+
+
+def composite_host(surface: np.ndarray, tile: int, rank: int, world: int, all_gather) -> None:
+    """CPU restatement of TileComposite.run for the gloo tests: all_gather(send) -> list of buffers."""
+    slots = max_owned(surface.shape[1], surface.shape[0], tile, world)
+    send = pack_tiles_host(surface, tile, rank, world, slots)
+    for r, buf in enumerate(all_gather(send)):
+        if r != rank:
+            unpack_tiles_host(surface, buf, tile, r, world)
+
+
+class TileComposite:
+    """GPU composite of one registered render-target slot with torch.distributed (NCCL)."""
+
+    def __init__(self, rasterizer, width: int, height: int, tile: int, rank: int, world: int, device):
+        import torch
+        self.r, self.tile, self.rank, self.world = rasterizer, tile, rank, world
+        self.slots = max_owned(width, height, tile, world)
+        n = self.slots * tile * tile
+        self.send = torch.zeros(n, dtype=torch.int32, device=device)
+        self.recv = torch.zeros(world * n, dtype=torch.int32, device=device)
+        self.bytes_per_rank = n * 4
+
+    def run(self, slot: int) -> None:
+        """pack (CUDA kernel) -> NCCL all_gather over NVLink -> unpack peers' tiles (CUDA kernels).
+        The rasterizer must enqueue on torch's current stream (Rasterizer.setStream)."""
+        import torch.distributed as dist
+        from . import _lib
+        lib = _lib.load()
+        r, w = self.rank, self.world
+        _lib.check(lib.swr_pack_tiles(self.r.ctx, slot, r, w, self.tile, self.send.data_ptr()), "pack_tiles")
+        dist.all_gather_into_tensor(self.recv, self.send)
+        n = self.send.numel()
+        for peer in range(w):
+            if peer != r:
+                _lib.check(lib.swr_unpack_tiles(self.r.ctx, slot, peer, w, self.tile, self.recv.data_ptr() + peer * n * 4),
+                           "unpack_tiles")

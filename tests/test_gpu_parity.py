@@ -99,7 +99,7 @@ def test_multi_pass_equals_single_pass(oracle, renderers):
     from softwarerenderer_b200.api import SceneRenderer
     scene = S.config_c3(250, 200, 480, 270, ps=S.PS_COUNT_ID)
     sr = SceneRenderer(scene.width, scene.height)
-    sr.r.setScratchLimit(64 << 20)
+    sr.r.setScratchLimit(4 << 20)
     got = sr.render(scene)
     assert got["stats"].passes > 1
     check(got, oracle.run(scene, "oracle"), "multipass")

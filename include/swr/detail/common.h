@@ -56,6 +56,15 @@ SWR_HD int f2i(float a) { return (int)a; }
 SWR_HD float i2f(int a) { return (float)a; }
 #endif
 
+SWR_HD int ffs32(uint32_t v)
+{
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)v);
+#else
+    return __builtin_ffs((int)v);
+#endif
+}
+
 struct Box16 { int16_t x0, y0, x1, y1; };        // inclusive; dead when x0 > x1
 SWR_HD Box16 deadBox() { Box16 b; b.x0 = 32767; b.y0 = 32767; b.x1 = -32768; b.y1 = -32768; return b; }
 

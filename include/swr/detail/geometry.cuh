@@ -531,23 +531,47 @@ __global__ void __launch_bounds__(kGeomThreads) geometryKernel(const GeomArgs g)
     const int per = g.drawMode + 1;
     bool anyExtra = false;
 
-    for (int r = 0; r < kBatch / kGeomThreads; ++r) {
+    // the next round's indices are fetched while the current round computes (the vertex fetch
+    // depends on them, so this takes one DRAM round trip off every round's critical path)
+    constexpr int kRounds = kBatch / kGeomThreads;
+    int32_t cur[3] = { 0, 0, 0 }, nxt[3] = { 0, 0, 0 };
+    auto fetch = [&](int r, int32_t *dst) {
+        const int slot = r * kGeomThreads + tid;
+        if (slot < cnt) {
+            const int32_t *ip = g.indices + (size_t)(primBase + slot) * per;
+            dst[0] = ip[0];
+            if (per > 1) dst[1] = ip[1];
+            if (per > 2) dst[2] = ip[2];
+        }
+    };
+    fetch(0, cur);
+
+#pragma unroll 1
+    for (int r = 0; r < kRounds; ++r) {
+        if (r + 1 < kRounds) fetch(r + 1, nxt);
         const int slot = r * kGeomThreads + tid;
         const uint32_t rec = (uint32_t)(primBase + slot);
         Box16 box = deadBox();
         int extras = 0;
         if (slot < cnt) {
-            const int32_t *ip = g.indices + (size_t)rec * per;
+            const int32_t ip[3] = { cur[0], cur[1], cur[2] };
             const uint32_t ordinal = ord0 + (uint32_t)slot;
             if (g.drawMode == SWR_DRAW_TRIANGLE) {
                 V v0, v1, v2;
                 shadeVertex<VS>(g, ip[0], v0);
                 shadeVertex<VS>(g, ip[1], v1);
                 shadeVertex<VS>(g, ip[2], v2);
-                const int mask = outcode(v0.x, v0.y, v0.z, v0.w) | outcode(v1.x, v1.y, v1.z, v1.w) |
-                                 outcode(v2.x, v2.y, v2.z, v2.w);
+                const int m0 = outcode(v0.x, v0.y, v0.z, v0.w), m1 = outcode(v1.x, v1.y, v1.z, v1.w),
+                          m2 = outcode(v2.x, v2.y, v2.z, v2.w);
+                const int mask = m0 | m1 | m2;
                 if (mask == 0) {
                     box = emitClipTriangle<NA, NP>(g, rec, ordinal, v0, v1, v2);
+                } else if ((mask & -mask) & (m0 & m1 & m2)) {
+                    // Trivial reject, exactly as the reference computes it: the FIRST plane it clips
+                    // against (lowest flagged bit, VertexProcessor.cpp:237-242) has all three original
+                    // vertices outside (its distance a*x+b*y+c*z+d*w equals the outcode's w-x, x+w, ...
+                    // bit for bit on finite inputs), so that pass emits nothing (PolyClipper.cpp:64-74)
+                    // and the triangle is fully clipped.  No polygon is built.
                 } else {
                     V a[kMaxPoly], b[kMaxPoly], *poly;      // rare path: polygons live in local memory
                     a[0] = v0; a[1] = v1; a[2] = v2;
@@ -575,6 +599,7 @@ __global__ void __launch_bounds__(kGeomThreads) geometryKernel(const GeomArgs g)
         sExtraCnt[slot] = (uint16_t)extras;
         anyExtra |= extras > 0;
         publishGroup(g, box, rec >> 5, 2u * (uint32_t)batch);
+        cur[0] = nxt[0]; cur[1] = nxt[1]; cur[2] = nxt[2];
     }
 
     // ---- clipper fan extras: appended behind the batch's original slots, in primitive order

@@ -32,6 +32,16 @@
 namespace swr {
 namespace detail {
 
+#ifndef SWR_COVER_VARIANT
+#define SWR_COVER_VARIANT 1
+#endif
+#ifndef SWR_DENSE_MIN
+#define SWR_DENSE_MIN 32
+#endif
+#ifndef SWR_DENSE_PATH
+#define SWR_DENSE_PATH 1
+#endif
+
 constexpr int kQueue = 512;          // primitives per flush
 constexpr int kItems = 2048;         // (primitive, block) items per flush
 constexpr int kChunkList = 1024;
@@ -133,14 +143,15 @@ SWR_HD uint64_t coverBlock(const float4 h0, const float4 h1, const float4 h2, in
     const float thr[3] = { (flags & kTie0) ? negTiny : 0.0f, (flags & kTie1) ? negTiny : 0.0f, (flags & kTie2) ? negTiny : 0.0f };
     const float xf = fadd(i2f(gx), 0.5f), yf = fadd(i2f(gy), 0.5f);
     const float s = 7.0f;
-    float e00[3];
+    float e00[3], a7[3];
     bool in[4][3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
+        a7[k] = fmul(ea[k], s);
         e00[k] = fadd(fadd(fmul(ea[k], xf), fmul(eb[k], yf)), ec[k]);      // EdgeData.h:37-42
         const float e01 = fadd(e00[k], fmul(eb[k], s));                    // stepY(s)
-        const float e10 = fadd(e00[k], fmul(ea[k], s));                    // stepX(s)
-        const float e11 = fadd(e01, fmul(ea[k], s));
+        const float e10 = fadd(e00[k], a7[k]);                             // stepX(s)
+        const float e11 = fadd(e01, a7[k]);
         in[0][k] = e00[k] > thr[k]; in[1][k] = e01 > thr[k];
         in[2][k] = e10 > thr[k]; in[3][k] = e11 > thr[k];
     }
@@ -153,11 +164,13 @@ SWR_HD uint64_t coverBlock(const float4 h0, const float4 h1, const float4 h2, in
     }
     if (all == 4) return ~0ull;                                            // drawBlock<false>
     if (all == 0 && same) return 0ull;                                     // "special case": block skipped
+
+#if SWR_COVER_VARIANT == 1
+    // variant 1: row-by-row, exact row maxima from the full 7-add chains
     uint64_t mask = 0;
     float r0 = e00[0], r1 = e00[1], r2 = e00[2];
 #pragma unroll 1
     for (int yy = 0; yy < 8; ++yy) {
-        // last value of each edge's chain in this row (7 adds, the same ones the per-pixel walk does)
         float l0 = r0, l1 = r1, l2 = r2;
 #pragma unroll
         for (int xx = 0; xx < 7; ++xx) { l0 = fadd(l0, ea[0]); l1 = fadd(l1, ea[1]); l2 = fadd(l2, ea[2]); }
@@ -176,8 +189,64 @@ SWR_HD uint64_t coverBlock(const float4 h0, const float4 h1, const float4 h2, in
         }
         r0 = fadd(r0, eb[0]); r1 = fadd(r1, eb[1]); r2 = fadd(r2, eb[2]);
     }
+    (void)a7;
     return mask;
 }
+#else
+    // Pass 1 -- which rows can hold a covered pixel.  Row yy of edge k starts at the reference's
+    // row chain value r (e00 + b + b + ...) and its maximum is r when a <= 0, else the last chain
+    // value l = ((r + a) + a) ... (7 adds).  l is first bracketed by q = r + 7a with the proven
+    // bound |l - q| <= 2^-20 * max(|r|, |q|) (+ an absolute term for the subnormal range); only
+    // when that bracket straddles zero are the 7 adds actually performed.  Exact either way.
+    uint32_t live = 0;
+    {
+        float r[3] = { e00[0], e00[1], e00[2] };
+#pragma unroll
+        for (int yy = 0; yy < 8; ++yy) {
+            bool dead = false;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                if (ea[k] <= 0) {
+                    dead = dead || !(r[k] > thr[k]);
+                } else if (ea[k] > 0) {
+                    const float q = fadd(r[k], a7[k]);
+                    const float M = fmaxf(fabsf(r[k]), fabsf(q));
+                    const float d = fadd(fmul(M, 9.5367431640625e-07f), 1e-40f);
+                    if (fadd(q, d) < 0) {
+                        dead = true;
+                    } else if (!(fsub(q, d) > 0)) {
+                        float l = r[k];
+#pragma unroll
+                        for (int xx = 0; xx < 7; ++xx) l = fadd(l, ea[k]);
+                        dead = dead || !(l > thr[k]);
+                    }
+                }
+                r[k] = fadd(r[k], eb[k]);
+            }
+            if (!dead) live |= 1u << yy;
+        }
+    }
+
+    // Pass 2 -- the per-pixel walk of the live rows only (PixelShaderBase.h:68-92)
+    uint64_t mask = 0;
+    while (live) {
+        const int yy = ffs32(live) - 1;
+        live &= live - 1;
+        float v0 = e00[0], v1 = e00[1], v2 = e00[2];
+#pragma unroll
+        for (int sy = 0; sy < 7; ++sy)
+            if (sy < yy) { v0 = fadd(v0, eb[0]); v1 = fadd(v1, eb[1]); v2 = fadd(v2, eb[2]); }
+        uint32_t rowMask = 0;
+#pragma unroll
+        for (int xx = 0; xx < 8; ++xx) {
+            if (v0 > thr[0] && v1 > thr[1] && v2 > thr[2]) rowMask |= 1u << xx;
+            v0 = fadd(v0, ea[0]); v1 = fadd(v1, ea[1]); v2 = fadd(v2, ea[2]);
+        }
+        mask |= (uint64_t)rowMask << (yy * 8);
+    }
+    return mask;
+}
+#endif
 
 SWR_HD SpanHalf loadHalf(const float4 v, uint32_t y0, uint32_t y1)
 {
@@ -444,7 +513,7 @@ __global__ void __launch_bounds__(kTileThreads, 3) tileKernel(const TileArgs t)
     uint64_t *sScan = (uint64_t *)(smem + SM::offScan);
     Ctl *ctl = (Ctl *)(smem + SM::offCtl);
 
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int X0 = tx << TLOG, Y0 = ty << TLOG, X1 = X0 + T - 1, Y1 = Y0 + T - 1;
     int phase = 0;
     bool loaded = false;
@@ -539,55 +608,80 @@ __global__ void __launch_bounds__(kTileThreads, 3) tileKernel(const TileArgs t)
                     const int bx0 = rg & 0xff, by0 = (rg >> 8) & 0xff, nx = (int)((rg >> 16) & 0xff) - bx0 + 1;
                     m = sMasks[qItem[q] + (uint32_t)((by - by0) * nx + (bx - bx0))];
                 }
-                uint32_t fincl = __popcll(m);
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    uint32_t n = __shfl_up_sync(0xffffffffu, fincl, o);
-                    if (lane >= o) fincl += n;
-                }
-                const uint32_t fex = fincl - __popcll(m);
-                const uint32_t totalF = __shfl_sync(0xffffffffu, fincl, 31);
-                for (uint32_t fbase = 0; fbase < totalF; fbase += 32) {
-                    const uint32_t f = fbase + lane;
-                    const bool fvalid = f < totalF;
-                    int ol = 0;
-#pragma unroll
-                    for (int s = 16; s > 0; s >>= 1) {       // largest lane ol with fex[ol] <= f
-                        const int c = ol + s;
-                        const uint32_t e = __shfl_sync(0xffffffffu, fex, c & 31);
-                        if (c < 32 && e <= f) ol = c;
+                // One fragment of primitive `frec` at bit `fbit` of this block.
+                auto shadeOne = [&](uint32_t frec, int fbit) {
+                    const int xx = fbit & 7, yy = fbit >> 3;
+                    if (gx + xx >= t.rtWidth || gy + yy >= t.rtHeight) return;      // block sticks out of the surface
+                    p.rtOffset = (b * 64 + fbit) * 4;
+                    if (MODE == SWR_DRAW_TRIANGLE) {
+                        shadeTriangleFragment<PS>(t, frec, gx, gy, xx, yy, p);
+                        ++frags;
+                    } else if (MODE == SWR_DRAW_LINE) {
+                        frags += shadeLineFragments<PS>(t, frec, gx + xx, gy + yy, p);
+                    } else {
+                        shadePointFragment<PS>(t, frec, gx + xx, gy + yy, p);
+                        ++frags;
                     }
-                    const uint64_t om = __shfl_sync(0xffffffffu, m, ol);
-                    const uint32_t orec = __shfl_sync(0xffffffffu, rec, ol);
-                    const uint32_t oex = __shfl_sync(0xffffffffu, fex, ol);
-                    const int bit = fvalid ? nthSetBit64(om, (int)(f - oex)) : 0;
-                    // fragments of different primitives on the same pixel run in emission order
-                    const int first = __shfl_sync(0xffffffffu, ol, 0);
-                    int rank = 0, maxRank = 0;
-                    if (!__all_sync(0xffffffffu, !fvalid || ol == first)) {
-                        const uint32_t peers = __match_any_sync(0xffffffffu, fvalid ? bit : 64 + lane);
-                        rank = __popc(peers & ((1u << lane) - 1u));
-                        maxRank = rank;
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) maxRank = max(maxRank, __shfl_xor_sync(0xffffffffu, maxRank, o));
-                    }
-                    const int xx = bit & 7, yy = bit >> 3;
-                    const bool onTarget = fvalid && gx + xx < t.rtWidth && gy + yy < t.rtHeight;
-                    p.rtOffset = (b * 64 + bit) * 4;
-                    for (int r = 0; r <= maxRank; ++r) {
-                        if (onTarget && rank == r) {
-                            if (MODE == SWR_DRAW_TRIANGLE) {
-                                shadeTriangleFragment<PS>(t, orec, gx, gy, xx, yy, p);
-                                ++frags;
-                            } else if (MODE == SWR_DRAW_LINE) {
-                                frags += shadeLineFragments<PS>(t, orec, gx + xx, gy + yy, p);
-                            } else {
-                                shadePointFragment<PS>(t, orec, gx + xx, gy + yy, p);
-                                ++frags;
-                            }
-                        }
+                };
+
+                // Items are consumed in lane (= queue) order.  A DENSE item (>= SWR_DENSE_MIN covered pixels) is
+                // shaded on its own with lane <-> pixel fixed: no search, no conflict detection, and a
+                // pixel always meets the same lane.  A run of SPARSE items (tiny triangles) is packed,
+                // 32 fragments per round, one lane per fragment.
+                const uint32_t validMask = __ballot_sync(0xffffffffu, ivalid);
+                const uint32_t denseMask = SWR_DENSE_PATH ? __ballot_sync(0xffffffffu, __popcll(m) >= SWR_DENSE_MIN) : 0u;
+                const int nvalid = __popc(validMask);
+                int pos = 0;
+                while (pos < nvalid) {
+                    if ((denseMask >> pos) & 1u) {
+                        const uint64_t dm = __shfl_sync(0xffffffffu, m, pos);
+                        const uint32_t drec = __shfl_sync(0xffffffffu, rec, pos);
+                        if ((dm >> lane) & 1ull) shadeOne(drec, lane);
+                        if ((dm >> (lane + 32)) & 1ull) shadeOne(drec, lane + 32);
                         __syncwarp();
+                        ++pos;
+                        continue;
                     }
+                    // sparse run [pos, runEnd)
+                    const uint32_t after = denseMask >> pos;
+                    const int runEnd = after ? min(nvalid, pos + (__ffs((int)after) - 1)) : nvalid;
+                    const uint64_t mr = (lane >= pos && lane < runEnd) ? m : 0ull;
+                    uint32_t fincl = __popcll(mr);
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        uint32_t n = __shfl_up_sync(0xffffffffu, fincl, o);
+                        if (lane >= o) fincl += n;
+                    }
+                    const uint32_t fex = fincl - __popcll(mr);
+                    const uint32_t totalF = __shfl_sync(0xffffffffu, fincl, 31);
+                    for (uint32_t fbase = 0; fbase < totalF; fbase += 32) {
+                        const uint32_t f = fbase + lane;
+                        const bool fvalid = f < totalF;
+                        int ol = 0;
+#pragma unroll
+                        for (int sft = 16; sft > 0; sft >>= 1) {   // largest lane ol with fex[ol] <= f
+                            const int c = ol + sft;
+                            const uint32_t e = __shfl_sync(0xffffffffu, fex, c & 31);
+                            if (c < 32 && e <= f) ol = c;
+                        }
+                        const uint64_t om = __shfl_sync(0xffffffffu, mr, ol);
+                        const uint32_t orec = __shfl_sync(0xffffffffu, rec, ol);
+                        const uint32_t oex = __shfl_sync(0xffffffffu, fex, ol);
+                        const int bit = fvalid ? nthSetBit64(om, (int)(f - oex)) : 0;
+                        // fragments of different primitives on the same pixel run in emission order
+                        const int first = __shfl_sync(0xffffffffu, ol, 0);
+                        int rank = 0, maxRank = 0;
+                        if (!__all_sync(0xffffffffu, !fvalid || ol == first)) {
+                            const uint32_t peers = __match_any_sync(0xffffffffu, fvalid ? bit : 64 + lane);
+                            rank = __popc(peers & ((1u << lane) - 1u));
+                            maxRank = __reduce_max_sync(0xffffffffu, rank);
+                        }
+                        for (int r = 0; r <= maxRank; ++r) {
+                            if (fvalid && rank == r) shadeOne(orec, bit);
+                            __syncwarp();
+                        }
+                    }
+                    pos = runEnd;
                 }
             }
         }

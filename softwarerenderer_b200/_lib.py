@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libswr_b200.so")
+# SWR_LIB_VARIANT selects an experimental build (make VARIANT=_x EXTRA=-D...); unset = the product
+LIB_PATH = os.path.join(HERE, "libswr_b200" + os.environ.get("SWR_LIB_VARIANT", "") + ".so")
 
 MAX_RENDER_TARGETS = 12
 MAX_UNIFORM_BYTES = 1024

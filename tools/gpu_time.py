@@ -59,8 +59,13 @@ def timed(scene, tile, reps=5, check=False):
 
 
 if __name__ == "__main__":
-    args = [a for a in sys.argv[1:] if not a.startswith("--")]
-    tiles = [int(sys.argv[sys.argv.index("--tile") + 1])] if "--tile" in sys.argv else [32, 64]
+    argv = list(sys.argv[1:])
+    tiles = [32, 64]
+    if "--tile" in argv:
+        i = argv.index("--tile")
+        tiles = [int(argv[i + 1])]
+        del argv[i:i + 2]
+    args = [a for a in argv if not a.startswith("--")]
     for name in args or ["c0", "c0b", "c2", "c3"]:
         sc = SCENES[name]()
         for tile in tiles:

@@ -36,7 +36,13 @@ constexpr int kGroup = 32;                       // records per group AABB
 constexpr int kMaxPoly = SWR_MAX_POLY;
 constexpr int kMaxFan = kMaxPoly - 2;            // triangles per clipped input triangle
 constexpr int kGeomThreads = 256;
-constexpr int kTileThreads = 256;
+#ifndef SWR_TILE_THREADS
+#define SWR_TILE_THREADS 512
+#endif
+#ifndef SWR_TILE_MINB
+#define SWR_TILE_MINB 2
+#endif
+constexpr int kTileThreads = SWR_TILE_THREADS;
 
 // ---- exact fp32: never contracted into FMA, whatever flags the including TU is built with ----
 #if defined(__CUDA_ARCH__)
@@ -134,6 +140,7 @@ struct TileArgs {
     int32_t scMinX, scMinY, scMaxX, scMaxY;
     unsigned long long *fragCounter;
     const uint32_t *errorFlag;
+    uint32_t *tileStats;             // optional debug: 4 words per tile {globaltimer ns start, ns duration, primitives, fragments}
 };
 
 // number of floats of one params record

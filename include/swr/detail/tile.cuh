@@ -42,8 +42,14 @@ namespace detail {
 #define SWR_DENSE_PATH 1
 #endif
 
-constexpr int kQueue = 512;          // primitives per flush
-constexpr int kItems = 2048;         // (primitive, block) items per flush
+#ifndef SWR_QUEUE
+#define SWR_QUEUE 1024
+#endif
+#ifndef SWR_ITEMS
+#define SWR_ITEMS 4096
+#endif
+constexpr int kQueue = SWR_QUEUE;    // primitives per flush
+constexpr int kItems = SWR_ITEMS;    // (primitive, block) items per flush
 constexpr int kChunkList = 1024;
 constexpr int kGroupList = 1024;
 constexpr int kTileWarps = kTileThreads / 32;
@@ -490,7 +496,7 @@ SWR_D void moveTile(const TileArgs &t, char *rtSmem, int X0, int Y0)
 
 // ---- the kernel -----------------------------------------------------------------------------------
 template <class PS, int MODE, int TLOG>
-__global__ void __launch_bounds__(kTileThreads, 3) tileKernel(const TileArgs t)
+__global__ void __launch_bounds__(kTileThreads, SWR_TILE_MINB) tileKernel(const TileArgs t)
 {
     typedef PsTraits<PS> TR;
     typedef TileSmem<TLOG, TR::NRT> SM;
@@ -517,12 +523,15 @@ __global__ void __launch_bounds__(kTileThreads, 3) tileKernel(const TileArgs t)
     const int X0 = tx << TLOG, Y0 = ty << TLOG, X1 = X0 + T - 1, Y1 = Y0 + T - 1;
     int phase = 0;
     bool loaded = false;
-    uint32_t nGroup = 0, nQ = 0, nItems = 0;
+    uint32_t nGroup = 0, nQ = 0, nItems = 0, primsSeen = 0;
     unsigned long long frags = 0;
+    unsigned long long tStart = 0;
+    if (t.tileStats && tid == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tStart));
 
     // ---- flush: coverage (A) + shading (B) of the queued primitives -----------------------------
     auto flushQueue = [&]() {
         if (nQ == 0) return;
+        primsSeen += nQ;
         if (tid == 0) { qItem[nQ] = nItems; ctl->nextBlock = 0; }
         for (int i = tid; i < NB * QW; i += kTileThreads) sBlockmap[i] = 0;
         if (!loaded) {
@@ -577,7 +586,10 @@ __global__ void __launch_bounds__(kTileThreads, 3) tileKernel(const TileArgs t)
             if (b >= NB) break;
             const int bx = b % BPR, by = b / BPR;
             const int gx = X0 + bx * 8, gy = Y0 + by * 8;
-            const uint32_t bm = lane < QW ? sBlockmap[b * QW + lane] : 0u;
+            // the block's bitmap over the queue, 32 words (1024 queue entries) at a time, in order
+#pragma unroll 1
+            for (int wc = 0; wc < QW; wc += 32) {
+            const uint32_t bm = wc + lane < QW ? sBlockmap[b * QW + wc + lane] : 0u;
             uint32_t wincl = __popc(bm);
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -595,14 +607,14 @@ __global__ void __launch_bounds__(kTileThreads, 3) tileKernel(const TileArgs t)
                 for (int s = 16; s > 0; s >>= 1) {           // largest word wl with wex[wl] <= j
                     const int c = wl + s;
                     const uint32_t e = __shfl_sync(0xffffffffu, wex, c & 31);
-                    if (c < QW && e <= j) wl = c;
+                    if (wc + c < QW && e <= j) wl = c;
                 }
                 const uint32_t wbm = __shfl_sync(0xffffffffu, bm, wl);
                 const uint32_t wbase = __shfl_sync(0xffffffffu, wex, wl);
                 uint32_t q = 0, rec = 0;
                 uint64_t m = 0;
                 if (ivalid) {
-                    q = (uint32_t)wl * 32u + (uint32_t)nthSetBit32(wbm, (int)(j - wbase));
+                    q = (uint32_t)(wc + wl) * 32u + (uint32_t)nthSetBit32(wbm, (int)(j - wbase));
                     rec = qRec[q];
                     const uint32_t rg = qRange[q];
                     const int bx0 = rg & 0xff, by0 = (rg >> 8) & 0xff, nx = (int)((rg >> 16) & 0xff) - bx0 + 1;
@@ -684,6 +696,7 @@ __global__ void __launch_bounds__(kTileThreads, 3) tileKernel(const TileArgs t)
                     pos = runEnd;
                 }
             }
+            }   // word chunks
         }
         __syncthreads();
         nQ = 0;
@@ -816,6 +829,16 @@ __global__ void __launch_bounds__(kTileThreads, 3) tileKernel(const TileArgs t)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) frags += __shfl_xor_sync(0xffffffffu, frags, o);
     if (lane == 0 && frags) atomicAdd(t.fragCounter, frags);
+    if (t.tileStats) {
+        if (lane == 0 && frags) atomicAdd(&t.tileStats[blockIdx.x * 4 + 3], (uint32_t)frags);
+        if (tid == 0) {
+            unsigned long long tEnd;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tEnd));
+            t.tileStats[blockIdx.x * 4 + 0] = (uint32_t)tStart;
+            t.tileStats[blockIdx.x * 4 + 1] = (uint32_t)(tEnd - tStart);
+            t.tileStats[blockIdx.x * 4 + 2] = primsSeen;
+        }
+    }
 }
 
 template <class PS, int MODE, int TLOG>

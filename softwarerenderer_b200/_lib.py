@@ -69,6 +69,8 @@ SYMBOLS = [
     ("swr_unpack_tiles", C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     ("swr_owned_tile_count", C.c_int64, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     ("swr_debug_enable_stream", C.c_int, [_P, C.c_int]),
+    ("swr_debug_enable_tile_stats", C.c_int, [_P, C.c_int]),
+    ("swr_debug_read_tile_stats", C.c_int64, [_P, _P, C.c_int64]),
     ("swr_debug_read_stream", C.c_int64, [_P, _P, _P, _P, C.c_int64]),
 ]
 

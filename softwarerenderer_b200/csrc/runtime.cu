@@ -121,7 +121,9 @@ struct swr_context {
     size_t scratchLimit = (size_t)16 << 30;
 
     // scratch
-    DevBuf bbox, gbox, head, params, span, tilemap, extra, counters, dbgVerts, stageIdx, l2flush, ownedIdx;
+    DevBuf bbox, gbox, head, params, span, tilemap, extra, counters, dbgVerts, stageIdx, l2flush, ownedIdx, tileStats;
+    bool debugTileStats = false;
+    int lastTiles = 0;
     bool countersInit = false;
     int ownedKey[5] = { 0, 0, 0, 0, 0 };   // {tile size, rank, world, width, height} of ownedIdx
     DevBuf stageAttrib[SWR_MAX_VERTEX_ATTRIBS];
@@ -242,7 +244,7 @@ __global__ void fill32Kernel(uint32_t *dst, uint32_t value, size_t count)
 
 int chooseTileShift(const swr_context *c, int renderTargets)
 {
-    auto fits64 = [&]() { return (size_t)renderTargets * 64 * 64 * 4 + 48 * 1024 <= (size_t)227 * 1024; };
+    auto fits64 = [&]() { return (size_t)renderTargets * 64 * 64 * 4 + 80 * 1024 <= (size_t)227 * 1024; };
     int req = c->tileSizeReq;
     if (req == 0) {
         const char *env = getenv("SWR_TILE_SIZE");
@@ -401,6 +403,12 @@ int drawCommon(swr_context *c, int drawMode, size_t count, const int32_t *indice
     t.scMinX = c->scMinX; t.scMinY = c->scMinY; t.scMaxX = c->scMaxX; t.scMaxY = c->scMaxY;
     t.fragCounter = &dc->fragments;
     t.errorFlag = &dc->errorFlag;
+    if (c->debugTileStats) {
+        if (int rc = c->tileStats.reserve((size_t)tilesX * tilesY * 16)) return rc;
+        CUDA_TRY(cudaMemsetAsync(c->tileStats.ptr, 0, (size_t)tilesX * tilesY * 16, c->stream));
+        t.tileStats = static_cast<uint32_t *>(c->tileStats.ptr);
+        c->lastTiles = tilesX * tilesY;
+    }
 
     swr_launch_fn geomLaunch = rasterVerts ? &launchRasterList : vs->launch_geometry;
     swr_launch_fn tileLaunch = ps->launch_tiles[drawMode][tileShift - 5];
@@ -478,7 +486,7 @@ void swr_destroy(swr_context *c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     DevBuf *bufs[] = { &c->bbox, &c->gbox, &c->head, &c->params, &c->span, &c->tilemap, &c->extra, &c->counters,
-                       &c->dbgVerts, &c->stageIdx, &c->l2flush, &c->ownedIdx };
+                       &c->dbgVerts, &c->stageIdx, &c->l2flush, &c->ownedIdx, &c->tileStats };
     for (DevBuf *b : bufs) b->release();
     for (int i = 0; i < SWR_MAX_VERTEX_ATTRIBS; ++i) c->stageAttrib[i].release();
     if (c->hostFlags) cudaFreeHost(c->hostFlags);
@@ -827,6 +835,24 @@ int swr_pack_tiles(swr_context *c, int slot, int rank, int world, int tile_size,
 int swr_unpack_tiles(swr_context *c, int slot, int rank, int world, int tile_size, const void *src_device)
 {
     return exchangeTiles(c, slot, rank, world, tile_size, const_cast<void *>(src_device), false);
+}
+
+int swr_debug_enable_tile_stats(swr_context *c, int enable)
+{
+    if (!c) return fail(-1, "null context");
+    c->debugTileStats = enable != 0;
+    return 0;
+}
+
+int64_t swr_debug_read_tile_stats(swr_context *c, uint32_t *out, int64_t cap_tiles)
+{
+    if (!c || !out) return fail(-1, "null argument");
+    if (int rc = setDevice(c)) return rc;
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) return fail(-100, "sync failed");
+    if (!c->tileStats.ptr) return 0;
+    const int64_t n = std::min<int64_t>(cap_tiles, c->lastTiles);
+    if (cudaMemcpy(out, c->tileStats.ptr, (size_t)n * 16, cudaMemcpyDeviceToHost) != cudaSuccess) return fail(-100, "copy failed");
+    return c->lastTiles;
 }
 
 int swr_debug_enable_stream(swr_context *c, int enable)

@@ -147,3 +147,38 @@ def test_tile_partition_union_equals_full(oracle, renderers):
         sr.close()
     assert frags == want["fragments"]
     assert not common.diff_buffers(acc, want, ("count", "prim_id"))
+
+
+def test_gpu_pack_unpack_matches_host_layout(renderers):
+    """swr_pack_tiles / swr_unpack_tiles produce exactly the layout of softwarerenderer_b200.dist."""
+    from softwarerenderer_b200 import _lib, dist as D
+    from softwarerenderer_b200 import api
+    lib = _lib.load()
+    w, h, tile, world = 480, 270, 32, 4
+    sr = renderers(w, h)
+    rng = np.random.default_rng(1)
+    surf = rng.integers(0, 1 << 32, size=(h, w), dtype=np.uint32)
+    sr.r.upload(sr.targets.ptr(api.RT_COLOR), surf)
+    slots = D.max_owned(w, h, tile, world)
+    buf = sr.r.alloc(slots * tile * tile * 4)
+    for rank in range(world):
+        sr.r.fill32(buf, 0, slots * tile * tile)
+        _lib.check(lib.swr_pack_tiles(sr.r.ctx, api.RT_COLOR, rank, world, tile, buf), "pack")
+        got = np.empty((slots, tile, tile), dtype=np.uint32)
+        sr.r.download(buf, got)
+        sr.r.finish()
+        want = D.pack_tiles_host(surf, tile, rank, world, slots)
+        n = len(D.owned_tiles(w, h, tile, rank, world))
+        assert np.array_equal(got[:n], want[:n]), rank
+    # unpack every rank's tiles of a second image into the (cleared) surface
+    surf2 = rng.integers(0, 1 << 32, size=(h, w), dtype=np.uint32)
+    sr.r.fill32(sr.targets.ptr(api.RT_COLOR), 0, w * h)
+    for rank in range(world):
+        packed = D.pack_tiles_host(surf2, tile, rank, world, slots)
+        sr.r.upload(buf, packed)
+        _lib.check(lib.swr_unpack_tiles(sr.r.ctx, api.RT_COLOR, rank, world, tile, buf), "unpack")
+    out = np.empty((h, w), dtype=np.uint32)
+    sr.r.download(sr.targets.ptr(api.RT_COLOR), out)
+    sr.r.finish()
+    assert np.array_equal(out, surf2)
+    sr.r.free(buf)

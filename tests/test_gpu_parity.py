@@ -182,3 +182,18 @@ def test_gpu_pack_unpack_matches_host_layout(renderers):
     sr.r.finish()
     assert np.array_equal(out, surf2)
     sr.r.free(buf)
+
+
+def test_cpp_crtp_example_benchmark():
+    """examples/benchmark.cu: user-written CRTP shaders in their own TU (built without -fmad=false),
+    through the C++ mirror of the reference API; fragment counts are the reference's own."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "bin", "benchmark")
+    if not os.path.exists(exe):
+        pytest.skip("examples not built")
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    assert "fragments 240235639 covered 76182" in out.stdout, out.stdout
+    out = subprocess.run([exe, "block"], capture_output=True, text=True, timeout=120)
+    assert "fragments 240235776 covered 76226" in out.stdout, out.stdout

@@ -170,6 +170,11 @@ def run_reference_arm(args):
 
 # ------------------------------------------------------------------------------------------------ GPU arm
 def run_gpu_arm(args):
+    # NCCL and friends write banners straight to fd 1; the contract is ONE JSON line on stdout, so
+    # everything else is sent to stderr and the line goes to the saved descriptor at the end.
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     from softwarerenderer_b200 import api
@@ -349,7 +354,8 @@ def run_gpu_arm(args):
         }
         if cpu_desc is not None:
             line["cpu_baseline"] = dict(cpu_desc, value=cpu_fps, unit=UNIT, triangles_per_s=cpu_tps)
-        print(json.dumps(line), flush=True)
+        real_stdout.write(json.dumps(line) + "\n")
+        real_stdout.flush()
 
     if world > 1:
         dist.destroy_process_group()

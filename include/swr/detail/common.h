@@ -117,6 +117,7 @@ struct GeomArgs {
     uint32_t extrasEnd;              // capacity end (record index)
     uint32_t *errorFlag;
     float *dbgVerts;                 // optional: 12 floats per record (3 x xyzw, screen space)
+    int32_t rank, world;             // sort-first: records that touch no tile owned by this rank are dropped
 };
 
 // Arguments of the tile kernel.
@@ -156,6 +157,22 @@ SWR_HD int paramFloats(int drawMode, int nA, int nP, int useZ, int useW)
 }
 
 SWR_HD bool tileOwned(int tx, int ty, int rank, int world) { return world <= 1 || ((tx + 3 * ty) % world) == rank; }
+
+// Does the pixel box touch a tile owned by `rank`?  (owner = (tx + 3 ty) mod world: any `world`
+// consecutive tiles of a row contain every owner, so only narrow boxes need the loop.)
+SWR_HD bool boxTouchesOwnedTile(const Box16 b, int tileShift, int tilesX, int tilesY, int rank, int world)
+{
+    if (world <= 1) return true;
+    int tx0 = b.x0 >> tileShift, ty0 = b.y0 >> tileShift, tx1 = b.x1 >> tileShift, ty1 = b.y1 >> tileShift;
+    if (tx1 > tilesX - 1) tx1 = tilesX - 1;
+    if (ty1 > tilesY - 1) ty1 = tilesY - 1;
+    if (tx0 > tx1 || ty0 > ty1) return false;
+    if (tx1 - tx0 + 1 >= world) return true;
+    for (int ty = ty0; ty <= ty1; ++ty)
+        for (int tx = tx0; tx <= tx1; ++tx)
+            if (tileOwned(tx, ty, rank, world)) return true;
+    return false;
+}
 
 } // namespace detail
 } // namespace swr

@@ -304,6 +304,9 @@ SWR_HD Box16 emitScreenTriangle(const GeomArgs &g, uint32_t rec, uint32_t ordina
         if (box.x0 > box.x1) return box;
     }
 
+    // sort-first: another rank rasterizes every tile this triangle touches -> no record here
+    if (!boxTouchesOwnedTile(box, g.tileShift, g.tilesX, g.tilesY, g.rank, g.world)) return deadBox();
+
     uint32_t flags = (e0.tie ? kTie0 : 0u) | (e1.tie ? kTie1 : 0u) | (e2.tie ? kTie2 : 0u) | (span ? kModeSpan : 0u);
     float4 *hd = g.head + (size_t)rec * 3;
     hd[0] = mkf4(e0.a, e0.b, e0.c, e1.a);
@@ -388,6 +391,7 @@ SWR_HD Box16 emitScreenLine(const GeomArgs &g, uint32_t rec, uint32_t ordinal, c
     Box16 box = makeBox(imax(imin(ix0, ix1) - 2, g.scMinX), imax(imin(iy0, iy1) - 2, g.scMinY),
                         imin(imax(ix0, ix1) + 2, g.scMaxX - 1), imin(imax(iy0, iy1) + 2, g.scMaxY - 1));
     if (box.x0 > box.x1) return box;
+    if (!boxTouchesOwnedTile(box, g.tileShift, g.tilesX, g.tilesY, g.rank, g.world)) return deadBox();
     const float fs = i2f(steps);
     float4 *hd = g.head + (size_t)rec * 3;
     hd[0] = mkf4(v0.x, v0.y, fdiv(fsub(v1.x, v0.x), fs), fdiv(fsub(v1.y, v0.y), fs));
@@ -417,6 +421,7 @@ SWR_HD Box16 emitScreenPoint(const GeomArgs &g, uint32_t rec, uint32_t ordinal, 
     const int ix = f2i(v.x), iy = f2i(v.y);
     Box16 box = makeBox(ix, iy, ix, iy);
     if (box.x0 > box.x1) return box;
+    if (!boxTouchesOwnedTile(box, g.tileShift, g.tilesX, g.tilesY, g.rank, g.world)) return deadBox();
     float4 *hd = g.head + (size_t)rec * 3;
     hd[0] = mkf4(v.x, v.y, 0.0f, 0.0f);
     hd[1] = mkf4(0.0f, u2f(ordinal), 0.0f, 0.0f);

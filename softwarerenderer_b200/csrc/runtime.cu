@@ -252,8 +252,10 @@ int chooseTileShift(const swr_context *c, int renderTargets)
     }
     if (req == 64 && fits64()) return 6;
     if (req == 32) return 5;
+    // 64-pixel tiles amortise the binning scans better, 32-pixel tiles balance better: take 64 only
+    // when this rank still gets >= 1024 of them
     const long tiles64 = (long)((c->rtW + 63) / 64) * ((c->rtH + 63) / 64);
-    return (tiles64 >= 1024 && fits64()) ? 6 : 5;
+    return (tiles64 / (c->world > 0 ? c->world : 1) >= 1024 && fits64()) ? 6 : 5;
 }
 
 // One draw = one or more passes of {geometry kernel, tile kernel}.
@@ -388,6 +390,8 @@ int drawCommon(swr_context *c, int drawMode, size_t count, const int32_t *indice
     g.extrasEnd = (uint32_t)recCap;
     g.errorFlag = &dc->errorFlag;
     g.dbgVerts = c->debugStream ? static_cast<float *>(c->dbgVerts.ptr) : nullptr;
+    g.rank = c->rank;
+    g.world = c->world;
 
     TileArgs t;
     memset(&t, 0, sizeof(t));

@@ -9,6 +9,8 @@
 // -Xcompiler -ffp-contract=off; no kernel is launched.
 #include <cuda_runtime.h>
 
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -212,10 +214,15 @@ int run(swr_scene *s)
     t.scMinX = g.scMinX; t.scMinY = g.scMinY; t.scMaxX = g.scMaxX; t.scMaxY = g.scMaxY;
     PixelData p;
     memset(&p, 0, sizeof(p));
+    long statLive = 0, statSingle = 0, statSingleZero = 0, statItems = 0, statZeroItems = 0, statZeroPrims = 0;
     for (uint32_t rec : st.order) {
         const Box16 bb = st.bbox[rec];
         if (bb.x0 > bb.x1) continue;
         s->primitives_out++;
+        const bool single = (bb.x0 >> 3) == (bb.x1 >> 3) && (bb.y0 >> 3) == (bb.y1 >> 3);
+        const uint64_t fragsBefore = s->fragments;
+        statLive++;
+        statSingle += single;
         for (int gy = bb.y0 & ~7; gy <= bb.y1; gy += 8) {
             for (int gx = bb.x0 & ~7; gx <= bb.x1; gx += 8) {
                 uint64_t m;
@@ -229,6 +236,8 @@ int run(swr_scene *s)
                     const int lx = f2i(h0.x) - gx, ly = f2i(h0.y) - gy;
                     m = ((unsigned)lx < 8u && (unsigned)ly < 8u) ? 1ull << (ly * 8 + lx) : 0ull;
                 }
+                statItems++;
+                statZeroItems += m == 0;
                 for (int bit = 0; bit < 64; ++bit) {
                     if (!((m >> bit) & 1)) continue;
                     const int xx = bit & 7, yy = bit >> 3;
@@ -239,7 +248,12 @@ int run(swr_scene *s)
                 }
             }
         }
+        if (s->fragments == fragsBefore) { statZeroPrims++; statSingleZero += single; }
     }
+    if (getenv("HOSTCHECK_STATS"))
+        fprintf(stderr, "hostcheck stats: live %ld single-block %ld (%.1f%%) zero-fragment prims %ld (%.1f%%) of which single-block %ld; items %ld zero items %ld (%.1f%%)\n",
+                statLive, statSingle, 100.0 * statSingle / statLive, statZeroPrims, 100.0 * statZeroPrims / statLive, statSingleZero,
+                statItems, statZeroItems, 100.0 * statZeroItems / statItems);
     return (int)errorFlags[1];
 }
 

@@ -53,6 +53,8 @@ constexpr int kItems = SWR_ITEMS;    // (primitive, block) items per flush
 constexpr int kChunkList = 1024;
 constexpr int kGroupList = 1024;
 constexpr int kTileWarps = kTileThreads / 32;
+constexpr int kPruneMax = 16;        // primitives with at most this many (primitive, block) items get the emptiness pre-test
+static_assert(2 * kTileThreads >= kQueue, "the item re-indexing scan handles two queue entries per thread");
 
 template <int TLOG, int NRT>
 struct TileSmem {
@@ -66,7 +68,8 @@ struct TileSmem {
     static constexpr size_t offQRec = offBlockmap + (size_t)NB * QW * 4;
     static constexpr size_t offQRange = offQRec + (size_t)kQueue * 4;
     static constexpr size_t offQItem = offQRange + (size_t)kQueue * 4;
-    static constexpr size_t offChunkGroup = offQItem + (size_t)(kQueue + 1) * 4 + 12;
+    static constexpr size_t offQValid = offQItem + (size_t)(kQueue + 1) * 4 + 12;
+    static constexpr size_t offChunkGroup = offQValid + (size_t)kQueue * 4;
     static constexpr size_t offChunkPair = offChunkGroup + (size_t)kChunkList * 4;
     static constexpr size_t offGroupList = offChunkPair + (size_t)(kChunkList + 1) * 4 + 12;
     static constexpr size_t offScan = offGroupList + (size_t)kGroupList * 4;
@@ -253,6 +256,33 @@ SWR_HD uint64_t coverBlock(const float4 h0, const float4 h1, const float4 h2, in
     return mask;
 }
 #endif
+
+// Exact emptiness test of one 8x8 block (Block mode): for every edge the largest of the 64 per-pixel
+// chain values sits at pixel (a > 0 ? 7 : 0, b > 0 ? 7 : 0) -- the row-start chain is monotone in the
+// row, and a row's chain is monotone in the column and in its start value -- so if that one value,
+// computed by the reference's own additions, fails the edge's inside test, no pixel of the block can
+// pass: coverBlock would return 0.  ~60 instructions instead of a full coverBlock.
+SWR_HD bool blockMayBeCovered(const float4 h0, const float4 h1, const float4 h2, int gx, int gy)
+{
+    const float ea[3] = { h0.x, h0.w, h1.z }, eb[3] = { h0.y, h1.x, h1.w }, ec[3] = { h0.z, h1.y, h2.x };
+    const uint32_t flags = f2u(h2.y);
+    const float negTiny = u2f(0x80000001u);
+    const float thr[3] = { (flags & kTie0) ? negTiny : 0.0f, (flags & kTie1) ? negTiny : 0.0f, (flags & kTie2) ? negTiny : 0.0f };
+    const float xf = fadd(i2f(gx), 0.5f), yf = fadd(i2f(gy), 0.5f);
+    bool may = true;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float v = fadd(fadd(fmul(ea[k], xf), fmul(eb[k], yf)), ec[k]);
+        const bool up = eb[k] > 0, right = ea[k] > 0;
+#pragma unroll
+        for (int s = 0; s < 7; ++s) if (up) v = fadd(v, eb[k]);
+#pragma unroll
+        for (int s = 0; s < 7; ++s) if (right) v = fadd(v, ea[k]);
+        const bool ordered = (ea[k] <= 0 || right) && (eb[k] <= 0 || up);     // false only for NaN coefficients
+        if (ordered && !(v > thr[k])) may = false;
+    }
+    return may;
+}
 
 SWR_HD SpanHalf loadHalf(const float4 v, uint32_t y0, uint32_t y1)
 {
@@ -513,6 +543,7 @@ __global__ void __launch_bounds__(kTileThreads, SWR_TILE_MINB) tileKernel(const 
     uint32_t *qRec = (uint32_t *)(smem + SM::offQRec);
     uint32_t *qRange = (uint32_t *)(smem + SM::offQRange);
     uint32_t *qItem = (uint32_t *)(smem + SM::offQItem);
+    uint32_t *qValid = (uint32_t *)(smem + SM::offQValid);
     uint32_t *cGroup = (uint32_t *)(smem + SM::offChunkGroup);     // first group of each listed chunk
     uint32_t *cPair = (uint32_t *)(smem + SM::offChunkPair);       // exclusive prefix of group counts
     uint32_t *gList = (uint32_t *)(smem + SM::offGroupList);
@@ -532,13 +563,53 @@ __global__ void __launch_bounds__(kTileThreads, SWR_TILE_MINB) tileKernel(const 
     auto flushQueue = [&]() {
         if (nQ == 0) return;
         primsSeen += nQ;
-        if (tid == 0) { qItem[nQ] = nItems; ctl->nextBlock = 0; }
+        if (tid == 0) ctl->nextBlock = 0;
         for (int i = tid; i < NB * QW; i += kTileThreads) sBlockmap[i] = 0;
         if (!loaded) {
             moveTile<TLOG, TR::NRT, false>(t, rtSmem, X0, Y0);
             loaded = true;
         }
+
+        // A0: drop the (primitive, block) items whose block provably holds no covered pixel (about
+        // half of them on tiny-triangle meshes: the reference visits every block of the truncated
+        // bounding box).  qValid = bitmap over the primitive's items, row-major in its block range.
+        // Worth its barrier + scan only when primitives span several blocks each (big triangles).
+        const bool prune = MODE == SWR_DRAW_TRIANGLE && nItems >= 3u * nQ;
+        for (uint32_t q = tid; q < nQ; q += kTileThreads) {
+            const uint32_t rg = qRange[q];
+            const int bx0 = rg & 0xff, by0 = (rg >> 8) & 0xff, nx = (int)((rg >> 16) & 0xff) - bx0 + 1;
+            const int n = nx * ((int)(rg >> 24) - by0 + 1);
+            uint32_t valid = n >= 32 ? 0xffffffffu : (1u << n) - 1u;
+            if (prune && n <= kPruneMax) {
+                const uint32_t rec = qRec[q];
+                const float4 h2 = t.head[(size_t)rec * 3 + 2];
+                if (!(f2u(h2.y) & kModeSpan)) {
+                    const float4 h0 = t.head[(size_t)rec * 3], h1 = t.head[(size_t)rec * 3 + 1];
+                    valid = 0;
+                    for (int li = 0; li < n; ++li)
+                        if (blockMayBeCovered(h0, h1, h2, X0 + (bx0 + li % nx) * 8, Y0 + (by0 + li / nx) * 8)) valid |= 1u << li;
+                }
+            }
+            qValid[q] = valid;
+        }
+        if (!prune && tid == 0) qItem[nQ] = nItems;       // qItem already holds the prefix F3 computed
         __syncthreads();
+        if (prune) {   // re-index the surviving items: qItem = exclusive prefix of the per-primitive item counts
+            auto itemCount = [&](uint32_t q) -> uint32_t {
+                if (q >= nQ) return 0u;
+                const uint32_t rg = qRange[q];
+                const int n = ((int)((rg >> 16) & 0xff) - (int)(rg & 0xff) + 1) * ((int)(rg >> 24) - (int)((rg >> 8) & 0xff) + 1);
+                return n <= kPruneMax ? (uint32_t)__popc(qValid[q]) : (uint32_t)n;
+            };
+            const uint32_t c0 = itemCount(2 * tid), c1 = itemCount(2 * tid + 1);
+            uint64_t total;
+            const uint32_t ex = (uint32_t)blockScan((uint64_t)(c0 + c1), total, sScan, phase);
+            if (2u * tid < nQ) qItem[2 * tid] = ex;
+            if (2u * tid + 1 < nQ) qItem[2 * tid + 1] = ex + c0;
+            nItems = (uint32_t)total;
+            if (tid == 0) qItem[nQ] = nItems;
+            __syncthreads();
+        }
 
         // A: one thread per (primitive, block) item
         for (uint32_t it = tid; it < nItems; it += kTileThreads) {
@@ -549,7 +620,9 @@ __global__ void __launch_bounds__(kTileThreads, SWR_TILE_MINB) tileKernel(const 
             }
             const uint32_t q = lo, rec = qRec[q], rg = qRange[q];
             const int bx0 = rg & 0xff, by0 = (rg >> 8) & 0xff, nx = (int)((rg >> 16) & 0xff) - bx0 + 1;
-            const int li = (int)(it - qItem[q]);
+            const int nAll = nx * ((int)(rg >> 24) - by0 + 1);
+            const int k = (int)(it - qItem[q]);
+            const int li = nAll <= kPruneMax ? nthSetBit32(qValid[q], k) : k;     // k-th surviving item -> block
             const int bx = bx0 + li % nx, by = by0 + li / nx;
             const int gx = X0 + bx * 8, gy = Y0 + by * 8;
             uint64_t m;
@@ -618,7 +691,10 @@ __global__ void __launch_bounds__(kTileThreads, SWR_TILE_MINB) tileKernel(const 
                     rec = qRec[q];
                     const uint32_t rg = qRange[q];
                     const int bx0 = rg & 0xff, by0 = (rg >> 8) & 0xff, nx = (int)((rg >> 16) & 0xff) - bx0 + 1;
-                    m = sMasks[qItem[q] + (uint32_t)((by - by0) * nx + (bx - bx0))];
+                    const int nAll = nx * ((int)(rg >> 24) - by0 + 1);
+                    const int li = (by - by0) * nx + (bx - bx0);
+                    const int k = nAll <= kPruneMax ? __popc(qValid[q] & ((1u << li) - 1u)) : li;
+                    m = sMasks[qItem[q] + (uint32_t)k];
                 }
                 // One fragment of primitive `frec` at bit `fbit` of this block.
                 auto shadeOne = [&](uint32_t frec, int fbit) {

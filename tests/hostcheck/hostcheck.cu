@@ -214,6 +214,7 @@ int run(swr_scene *s)
     t.scMinX = g.scMinX; t.scMinY = g.scMinY; t.scMaxX = g.scMaxX; t.scMaxY = g.scMaxY;
     PixelData p;
     memset(&p, 0, sizeof(p));
+    long statPruned = 0, pruneViolations = 0;
     long statLive = 0, statSingle = 0, statSingleZero = 0, statItems = 0, statZeroItems = 0, statZeroPrims = 0;
     for (uint32_t rec : st.order) {
         const Box16 bb = st.bbox[rec];
@@ -229,7 +230,10 @@ int run(swr_scene *s)
                 const float4 h0 = t.head[(size_t)rec * 3], h1 = t.head[(size_t)rec * 3 + 1], h2 = t.head[(size_t)rec * 3 + 2];
                 if (s->draw_mode == 2) {
                     if (f2u(h2.y) & kModeSpan) m = coverSpan(t.span[(size_t)rec * 3], t.span[(size_t)rec * 3 + 1], t.span[(size_t)rec * 3 + 2], gx, gy, t.scMinX, t.scMaxX);
-                    else m = coverBlock(h0, h1, h2, gx, gy);
+                    else {
+                        m = coverBlock(h0, h1, h2, gx, gy);
+                        if (!blockMayBeCovered(h0, h1, h2, gx, gy)) { statPruned++; if (m != 0) pruneViolations++; }
+                    }
                 } else if (s->draw_mode == 1) {
                     m = coverLine(h0, h1, gx, gy, t);
                 } else {
@@ -254,6 +258,8 @@ int run(swr_scene *s)
         fprintf(stderr, "hostcheck stats: live %ld single-block %ld (%.1f%%) zero-fragment prims %ld (%.1f%%) of which single-block %ld; items %ld zero items %ld (%.1f%%)\n",
                 statLive, statSingle, 100.0 * statSingle / statLive, statZeroPrims, 100.0 * statZeroPrims / statLive, statSingleZero,
                 statItems, statZeroItems, 100.0 * statZeroItems / statItems);
+    if (getenv("HOSTCHECK_STATS")) fprintf(stderr, "hostcheck stats: items pruned by blockMayBeCovered %ld, violations %ld\n", statPruned, pruneViolations);
+    if (pruneViolations) return -77;      // the emptiness pre-test must never drop a covered block
     return (int)errorFlags[1];
 }
 

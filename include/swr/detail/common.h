@@ -141,7 +141,7 @@ struct TileArgs {
     int32_t scMinX, scMinY, scMaxX, scMaxY;
     unsigned long long *fragCounter;
     const uint32_t *errorFlag;
-    uint32_t *tileStats;             // optional debug: 4 words per tile {globaltimer ns start, ns duration, primitives, fragments}
+    uint32_t *tileStats;             // optional debug: 8 words per tile {globaltimer ns start, ns duration, primitives, fragments, A0/A/B clocks >> 4 of thread 0, 0}
 };
 
 // number of floats of one params record

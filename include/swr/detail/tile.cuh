@@ -557,12 +557,16 @@ __global__ void __launch_bounds__(kTileThreads, SWR_TILE_MINB) tileKernel(const 
     uint32_t nGroup = 0, nQ = 0, nItems = 0, primsSeen = 0;
     unsigned long long frags = 0;
     unsigned long long tStart = 0;
-    if (t.tileStats && tid == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tStart));
+    long long cycA0 = 0, cycA = 0, cycB = 0, cycMark = 0;      // debug: per-phase clocks of thread 0
+    uint32_t dbgFlush = 0;
+    const bool timing = t.tileStats != nullptr && tid == 0;
+    if (timing) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tStart));
 
     // ---- flush: coverage (A) + shading (B) of the queued primitives -----------------------------
     auto flushQueue = [&]() {
         if (nQ == 0) return;
         primsSeen += nQ;
+        if (timing) { cycMark = clock64(); ++dbgFlush; }
         if (tid == 0) ctl->nextBlock = 0;
         for (int i = tid; i < NB * QW; i += kTileThreads) sBlockmap[i] = 0;
         if (!loaded) {
@@ -611,6 +615,7 @@ __global__ void __launch_bounds__(kTileThreads, SWR_TILE_MINB) tileKernel(const 
             __syncthreads();
         }
 
+        if (timing) { const long long c = clock64(); cycA0 += c - cycMark; cycMark = c; }
         // A: one thread per (primitive, block) item
         for (uint32_t it = tid; it < nItems; it += kTileThreads) {
             uint32_t lo = 0, hi = nQ;                        // largest q with qItem[q] <= it
@@ -646,6 +651,7 @@ __global__ void __launch_bounds__(kTileThreads, SWR_TILE_MINB) tileKernel(const 
         }
         __syncthreads();
 
+        if (timing) { const long long c = clock64(); cycA += c - cycMark; cycMark = c; }
         // B: per block, in queue order, 32 fragments per round
         PixelData p;
         p.rtBase = rtSmem;
@@ -775,6 +781,7 @@ __global__ void __launch_bounds__(kTileThreads, SWR_TILE_MINB) tileKernel(const 
             }   // word chunks
         }
         __syncthreads();
+        if (timing) cycB += clock64() - cycMark;
         nQ = 0;
         nItems = 0;
     };
@@ -906,13 +913,17 @@ __global__ void __launch_bounds__(kTileThreads, SWR_TILE_MINB) tileKernel(const 
     for (int o = 16; o > 0; o >>= 1) frags += __shfl_xor_sync(0xffffffffu, frags, o);
     if (lane == 0 && frags) atomicAdd(t.fragCounter, frags);
     if (t.tileStats) {
-        if (lane == 0 && frags) atomicAdd(&t.tileStats[blockIdx.x * 4 + 3], (uint32_t)frags);
+        if (lane == 0 && frags) atomicAdd(&t.tileStats[blockIdx.x * 8 + 3], (uint32_t)frags);
         if (tid == 0) {
             unsigned long long tEnd;
             asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tEnd));
-            t.tileStats[blockIdx.x * 4 + 0] = (uint32_t)tStart;
-            t.tileStats[blockIdx.x * 4 + 1] = (uint32_t)(tEnd - tStart);
-            t.tileStats[blockIdx.x * 4 + 2] = primsSeen;
+            t.tileStats[blockIdx.x * 8 + 0] = (uint32_t)tStart;
+            t.tileStats[blockIdx.x * 8 + 1] = (uint32_t)(tEnd - tStart);
+            t.tileStats[blockIdx.x * 8 + 2] = primsSeen;
+            t.tileStats[blockIdx.x * 8 + 4] = (uint32_t)(cycA0 >> 4);
+            t.tileStats[blockIdx.x * 8 + 5] = (uint32_t)(cycA >> 4);
+            t.tileStats[blockIdx.x * 8 + 6] = (uint32_t)(cycB >> 4);
+            t.tileStats[blockIdx.x * 8 + 7] = dbgFlush;
         }
     }
 }

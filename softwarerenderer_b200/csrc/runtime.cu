@@ -408,8 +408,8 @@ int drawCommon(swr_context *c, int drawMode, size_t count, const int32_t *indice
     t.fragCounter = &dc->fragments;
     t.errorFlag = &dc->errorFlag;
     if (c->debugTileStats) {
-        if (int rc = c->tileStats.reserve((size_t)tilesX * tilesY * 16)) return rc;
-        CUDA_TRY(cudaMemsetAsync(c->tileStats.ptr, 0, (size_t)tilesX * tilesY * 16, c->stream));
+        if (int rc = c->tileStats.reserve((size_t)tilesX * tilesY * 32)) return rc;
+        CUDA_TRY(cudaMemsetAsync(c->tileStats.ptr, 0, (size_t)tilesX * tilesY * 32, c->stream));
         t.tileStats = static_cast<uint32_t *>(c->tileStats.ptr);
         c->lastTiles = tilesX * tilesY;
     }
@@ -855,7 +855,7 @@ int64_t swr_debug_read_tile_stats(swr_context *c, uint32_t *out, int64_t cap_til
     if (cudaStreamSynchronize(c->stream) != cudaSuccess) return fail(-100, "sync failed");
     if (!c->tileStats.ptr) return 0;
     const int64_t n = std::min<int64_t>(cap_tiles, c->lastTiles);
-    if (cudaMemcpy(out, c->tileStats.ptr, (size_t)n * 16, cudaMemcpyDeviceToHost) != cudaSuccess) return fail(-100, "copy failed");
+    if (cudaMemcpy(out, c->tileStats.ptr, (size_t)n * 32, cudaMemcpyDeviceToHost) != cudaSuccess) return fail(-100, "copy failed");
     return c->lastTiles;
 }
 

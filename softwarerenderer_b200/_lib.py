@@ -50,6 +50,7 @@ SYMBOLS = [
     ("swr_set_tile_partition", C.c_int, [_P, C.c_int, C.c_int]),
     ("swr_set_scratch_limit", C.c_int, [_P, C.c_size_t]),
     ("swr_set_stream", C.c_int, [_P, _P]),
+    ("swr_set_pipeline", C.c_int, [_P, C.c_int, C.c_int, C.c_int]),
     ("swr_draw_elements", C.c_int, [_P, C.c_int, C.c_size_t, _P]),
     ("swr_draw_raster_list", C.c_int, [_P, C.c_int, _P, C.c_size_t, _P, C.c_size_t]),
     ("swr_finish", C.c_int, [_P]),

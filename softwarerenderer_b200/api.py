@@ -132,6 +132,10 @@ class Rasterizer:
         """Enqueue on a caller-owned CUDA stream (e.g. torch.cuda.current_stream().cuda_stream); 0 = own stream."""
         _lib.check(lib.swr_set_stream(self._ctx, cuda_stream or None), "setStream")
 
+    def setPipeline(self, enable: bool = True, passes: int = 0, overlap_draws: bool = False):
+        """Geometry(k+1) under tiles(k): inside one draw (passes, 0 = automatic) and optionally across draws."""
+        _lib.check(lib.swr_set_pipeline(self._ctx, int(enable), int(passes), int(overlap_draws)), "setPipeline")
+
     def finish(self):
         _lib.check(lib.swr_finish(self._ctx), "finish")
 

@@ -94,11 +94,29 @@ bool isDevicePointer(const void *p)
 
 } // namespace
 
+// One set of per-pass scratch.  Two sets alternate so that the geometry kernel of pass k+1 (on the
+// auxiliary stream) overlaps the tile kernel of pass k (on the main stream).
+struct ScratchSet {
+    DevBuf bbox, gbox, head, params, span, tilemap, extra, counters;
+    cudaEvent_t geomDone = nullptr, tileDone = nullptr;
+    bool tilePending = false, countersInit = false;
+    size_t bytes() const { return bbox.bytes + gbox.bytes + head.bytes + params.bytes + span.bytes + tilemap.bytes + extra.bytes + counters.bytes; }
+    void release() { bbox.release(); gbox.release(); head.release(); params.release(); span.release(); tilemap.release(); extra.release(); counters.release(); }
+};
+
 struct swr_context {
     int device = 0;
-    cudaStream_t stream = nullptr;      // the stream draws are enqueued on
+    cudaStream_t stream = nullptr;      // main stream: tile kernels, everything the caller orders against
     cudaStream_t ownStream = nullptr;   // created by swr_create
-    cudaEvent_t evGeom0 = nullptr, evGeom1 = nullptr, evTile1 = nullptr, evTimer0 = nullptr, evTimer1 = nullptr;
+    cudaStream_t aux = nullptr;         // geometry kernels and their input staging
+    cudaEvent_t evGeom0 = nullptr, evGeom1 = nullptr, evTile0 = nullptr, evTile1 = nullptr, evTimer0 = nullptr, evTimer1 = nullptr,
+                evDrawStart = nullptr;
+    ScratchSet sets[2];
+    uint64_t passSeq = 0;
+    int lastSet = 0;
+    bool pipeline = false;              // geometry on the auxiliary stream (two scratch sets); see swr_set_pipeline
+    bool overlapDraws = false;          // ... and across draws (caller promises not to touch the inputs in between)
+    int passesHint = 0;
     bool haveDrawEvents = false;
 
     // VertexProcessor state (defaults VertexProcessor.cpp:29-35)
@@ -121,10 +139,9 @@ struct swr_context {
     size_t scratchLimit = (size_t)16 << 30;
 
     // scratch
-    DevBuf bbox, gbox, head, params, span, tilemap, extra, counters, dbgVerts, stageIdx, l2flush, ownedIdx, tileStats;
+    DevBuf dbgVerts, stageIdx, l2flush, ownedIdx, tileStats;
     bool debugTileStats = false;
     int lastTiles = 0;
-    bool countersInit = false;
     int ownedKey[5] = { 0, 0, 0, 0, 0 };   // {tile size, rank, world, width, height} of ownedIdx
     DevBuf stageAttrib[SWR_MAX_VERTEX_ATTRIBS];
     uint32_t *hostFlags = nullptr;   // pinned: error flag read-back
@@ -148,8 +165,7 @@ int setDevice(swr_context *c)
 
 size_t scratchBytes(const swr_context *c)
 {
-    size_t n = c->bbox.bytes + c->gbox.bytes + c->head.bytes + c->params.bytes + c->span.bytes + c->tilemap.bytes +
-               c->extra.bytes + c->counters.bytes + c->dbgVerts.bytes + c->stageIdx.bytes + c->l2flush.bytes + c->ownedIdx.bytes;
+    size_t n = c->sets[0].bytes() + c->sets[1].bytes() + c->dbgVerts.bytes + c->stageIdx.bytes + c->l2flush.bytes + c->ownedIdx.bytes;
     for (int i = 0; i < SWR_MAX_VERTEX_ATTRIBS; ++i) n += c->stageAttrib[i].bytes;
     return n;
 }
@@ -285,13 +301,22 @@ int drawCommon(swr_context *c, int drawMode, size_t count, const int32_t *indice
             if (!c->attribs[i].ptr) return fail(-8, "vertex attribute %d not set", i);
     }
 
+    // ---- streams: geometry-side work goes to the auxiliary stream.  Unless the caller opted into
+    // overlapping whole draws, it first waits for everything already enqueued on the main stream
+    // (so buffers the caller filled on that stream are visible to the vertex stage).
+    cudaStream_t gs = c->pipeline ? c->aux : c->stream;
+    if (c->pipeline && !c->overlapDraws) {
+        CUDA_TRY(cudaEventRecord(c->evDrawStart, c->stream));
+        CUDA_TRY(cudaStreamWaitEvent(gs, c->evDrawStart, 0));
+    }
+
     // ---- inputs: device memory in place, host memory staged
     GeomArgs g;
     memset(&g, 0, sizeof(g));
     const int32_t *devIndices = indices;
     if (!isDevicePointer(indices)) {
         if (int rc = c->stageIdx.reserve(count * sizeof(int32_t))) return rc;
-        CUDA_TRY(cudaMemcpyAsync(c->stageIdx.ptr, indices, nprims * per * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(c->stageIdx.ptr, indices, nprims * per * sizeof(int32_t), cudaMemcpyHostToDevice, gs));
         devIndices = static_cast<const int32_t *>(c->stageIdx.ptr);
     }
     if (rasterVerts) {
@@ -299,7 +324,7 @@ int drawCommon(swr_context *c, int drawMode, size_t count, const int32_t *indice
         if (!isDevicePointer(rasterVerts)) {
             const size_t bytes = rasterVertCount * 144;
             if (int rc = c->stageAttrib[0].reserve(bytes)) return rc;
-            CUDA_TRY(cudaMemcpyAsync(c->stageAttrib[0].ptr, rasterVerts, bytes, cudaMemcpyHostToDevice, c->stream));
+            CUDA_TRY(cudaMemcpyAsync(c->stageAttrib[0].ptr, rasterVerts, bytes, cudaMemcpyHostToDevice, gs));
             dv = c->stageAttrib[0].ptr;
         }
         g.rasterVerts = dv;
@@ -310,7 +335,7 @@ int drawCommon(swr_context *c, int drawMode, size_t count, const int32_t *indice
             if (!isDevicePointer(a.ptr)) {
                 if (a.bytes == 0) return fail(-9, "vertex attribute %d is host memory: its extent is required (bytes > 0)", i);
                 if (int rc = c->stageAttrib[i].reserve(a.bytes)) return rc;
-                CUDA_TRY(cudaMemcpyAsync(c->stageAttrib[i].ptr, a.ptr, a.bytes, cudaMemcpyHostToDevice, c->stream));
+                CUDA_TRY(cudaMemcpyAsync(c->stageAttrib[i].ptr, a.ptr, a.bytes, cudaMemcpyHostToDevice, gs));
                 dp = c->stageAttrib[i].ptr;
             }
             g.attribPtr[i] = dp;
@@ -320,11 +345,18 @@ int drawCommon(swr_context *c, int drawMode, size_t count, const int32_t *indice
 
     // ---- uniforms into the shader TUs' constant blocks
     if (c->uniformBytes) {
-        if (!rasterVerts && vs->set_uniforms && vs->set_uniforms(c->uniforms, c->uniformBytes, c->stream) != 0)
+        // A vertex and a pixel shader of the same translation unit share one uniform block: it is then
+        // written once, on the main stream, and the geometry stream waits for it.
+        const bool shared = !rasterVerts && ps->set_uniforms == vs->set_uniforms;
+        if (!rasterVerts && !shared && vs->set_uniforms && vs->set_uniforms(c->uniforms, c->uniformBytes, gs) != 0)
             return fail(-10, "uniform upload failed (vertex shader '%s')", vs->name);
-        if (ps->set_uniforms && (rasterVerts || ps->set_uniforms != vs->set_uniforms) &&
-            ps->set_uniforms(c->uniforms, c->uniformBytes, c->stream) != 0)
+        if (ps->set_uniforms && ps->set_uniforms(c->uniforms, c->uniformBytes, c->stream) != 0)
             return fail(-10, "uniform upload failed (pixel shader '%s')", ps->name);
+        if (shared && gs != c->stream) {
+            CUDA_TRY(cudaStreamSynchronize(gs));             // no geometry kernel may still read the old block
+            CUDA_TRY(cudaEventRecord(c->evDrawStart, c->stream));
+            CUDA_TRY(cudaStreamWaitEvent(gs, c->evDrawStart, 0));
+        }
     }
 
     // ---- pass plan
@@ -337,9 +369,20 @@ int drawCommon(swr_context *c, int drawMode, size_t count, const int32_t *indice
     const bool tri = drawMode == SWR_DRAW_TRIANGLE && !rasterVerts;
     const size_t recBytes = sizeof(Box16) + 48 + (size_t)paramStride * 4 + (needSpan ? 48 : 0) + (c->debugStream ? 48 : 0);
     const size_t perPrimWorst = recBytes * (tri ? (size_t)(1 + kMaxFan - 1) : 1) + 16;
-    size_t passPrims = c->scratchLimit / perPrimWorst;
+    size_t passPrims = (c->scratchLimit / (c->pipeline ? 2 : 1)) / perPrimWorst;   // pipelining alternates two scratch sets
     passPrims = std::max<size_t>(kBatch, passPrims / kBatch * kBatch);
     passPrims = std::min(passPrims, (nprims + kBatch - 1) / kBatch * kBatch);
+    if (c->pipeline) {
+        // big draws are cut into a few passes so that geometry(k+1) runs under tiles(k)
+        int want = c->passesHint;
+        if (want <= 0) {
+            const char *env = getenv("SWR_PASSES");
+            want = env ? atoi(env) : 1;   // measured: one pass per draw is fastest (every tile pass has its own tail)
+        }
+        want = std::max(1, std::min(want, 64));
+        const size_t per_pass = ((nprims + want - 1) / want + kBatch - 1) / kBatch * kBatch;
+        passPrims = std::min(passPrims, std::max<size_t>(kBatch, per_pass));
+    }
     const size_t firstsCap = passPrims;                                  // multiple of kBatch
     const size_t extrasCap = tri ? passPrims * (size_t)(kMaxFan - 1) : 0;
     const size_t recCap = firstsCap + extrasCap;
@@ -347,27 +390,26 @@ int drawCommon(swr_context *c, int drawMode, size_t count, const int32_t *indice
     const size_t passBatches = passPrims / kBatch;
     const int chunkWords = (int)((2 * passBatches + 31) / 32);
 
-    if (int rc = c->bbox.reserve(recCap * sizeof(Box16))) return rc;
-    if (int rc = c->gbox.reserve((recCap / kGroup + 1) * sizeof(Box16))) return rc;
-    if (int rc = c->head.reserve(recCap * 48)) return rc;
-    if (int rc = c->params.reserve(recCap * (size_t)paramStride * 4 + 16)) return rc;
-    if (needSpan) if (int rc = c->span.reserve(recCap * 48)) return rc;
-    if (int rc = c->tilemap.reserve((size_t)tilesX * tilesY * chunkWords * 4)) return rc;
-    if (int rc = c->extra.reserve(passBatches * sizeof(uint2))) return rc;
-    if (int rc = c->counters.reserve(sizeof(Counters))) return rc;
+    for (ScratchSet &ss : c->sets) {
+        if (int rc = ss.bbox.reserve(recCap * sizeof(Box16))) return rc;
+        if (int rc = ss.gbox.reserve((recCap / kGroup + 1) * sizeof(Box16))) return rc;
+        if (int rc = ss.head.reserve(recCap * 48)) return rc;
+        if (int rc = ss.params.reserve(recCap * (size_t)paramStride * 4 + 16)) return rc;
+        if (needSpan) if (int rc = ss.span.reserve(recCap * 48)) return rc;
+        if (int rc = ss.tilemap.reserve((size_t)tilesX * tilesY * chunkWords * 4)) return rc;
+        if (int rc = ss.extra.reserve(passBatches * sizeof(uint2))) return rc;
+        if (int rc = ss.counters.reserve(sizeof(Counters))) return rc;
+        if (!ss.countersInit) {
+            CUDA_TRY(cudaMemset(ss.counters.ptr, 0, sizeof(Counters)));
+            ss.countersInit = true;
+        }
+        if (!c->pipeline) break;                                         // without overlap only set 0 is used
+    }
     if (c->debugStream) if (int rc = c->dbgVerts.reserve(recCap * 48)) return rc;
     if (!c->hostFlags) {
         CUDA_TRY(cudaMallocHost((void **)&c->hostFlags, 64));
-        c->hostFlags[0] = 0;
+        c->hostFlags[0] = c->hostFlags[1] = 0;
     }
-    c->stats.scratch_bytes = scratchBytes(c);
-
-    Counters *dc = static_cast<Counters *>(c->counters.ptr);
-    if (!c->countersInit) {
-        CUDA_TRY(cudaMemsetAsync(dc, 0, sizeof(Counters), c->stream));
-        c->countersInit = true;
-    }
-    CUDA_TRY(cudaMemsetAsync(&dc->errorFlag, 0, sizeof(uint32_t), c->stream));
 
     g.drawMode = drawMode;
     g.px = c->px; g.py = c->py; g.ox = c->ox; g.oy = c->oy;
@@ -375,38 +417,25 @@ int drawCommon(swr_context *c, int drawMode, size_t count, const int32_t *indice
     g.cullMode = c->cullMode; g.rasterMode = c->rasterMode;
     g.scMinX = c->scMinX; g.scMinY = c->scMinY; g.scMaxX = c->scMaxX; g.scMaxY = c->scMaxY;
     g.nA = nA; g.nP = nP; g.useZ = useZ; g.useW = useW;
-    g.bbox = static_cast<Box16 *>(c->bbox.ptr);
-    g.gbox = static_cast<Box16 *>(c->gbox.ptr);
-    g.head = static_cast<float4 *>(c->head.ptr);
-    g.params = static_cast<float *>(c->params.ptr);
-    g.span = static_cast<float4 *>(c->span.ptr);
     g.paramStride = paramStride;
-    g.tilemap = static_cast<uint32_t *>(c->tilemap.ptr);
     g.chunkWords = chunkWords;
     g.tileShift = tileShift;
     g.tilesX = tilesX; g.tilesY = tilesY;
-    g.extra = static_cast<uint2 *>(c->extra.ptr);
-    g.extraAlloc = &dc->extraAlloc;
     g.extrasEnd = (uint32_t)recCap;
-    g.errorFlag = &dc->errorFlag;
     g.dbgVerts = c->debugStream ? static_cast<float *>(c->dbgVerts.ptr) : nullptr;
     g.rank = c->rank;
     g.world = c->world;
 
     TileArgs t;
     memset(&t, 0, sizeof(t));
-    t.bbox = g.bbox; t.gbox = g.gbox; t.head = g.head; t.params = g.params; t.span = g.span;
     t.paramStride = paramStride;
-    t.tilemap = g.tilemap; t.chunkWords = chunkWords;
-    t.extra = g.extra;
+    t.chunkWords = chunkWords;
     t.tilesX = tilesX; t.tilesY = tilesY;
     t.rank = c->rank; t.world = c->world;
     t.rtWidth = c->rtW; t.rtHeight = c->rtH;
     t.numRT = ps->render_targets;
     for (int s = 0; s < SWR_MAX_RENDER_TARGETS; ++s) t.rt[s] = c->rt[s];
     t.scMinX = c->scMinX; t.scMinY = c->scMinY; t.scMaxX = c->scMaxX; t.scMaxY = c->scMaxY;
-    t.fragCounter = &dc->fragments;
-    t.errorFlag = &dc->errorFlag;
     if (c->debugTileStats) {
         if (int rc = c->tileStats.reserve((size_t)tilesX * tilesY * 32)) return rc;
         CUDA_TRY(cudaMemsetAsync(c->tileStats.ptr, 0, (size_t)tilesX * tilesY * 32, c->stream));
@@ -418,24 +447,58 @@ int drawCommon(swr_context *c, int drawMode, size_t count, const int32_t *indice
     swr_launch_fn tileLaunch = ps->launch_tiles[drawMode][tileShift - 5];
     const uint32_t extrasBegin = (uint32_t)firstsCap;
 
-    CUDA_TRY(cudaEventRecord(c->evGeom0, c->stream));
+    CUDA_TRY(cudaEventRecord(c->evGeom0, gs));
+    bool firstPass = true;
     for (size_t first = 0; first < nprims; first += passPrims) {
         const size_t n = std::min(passPrims, nprims - first);
+        ScratchSet &ss = c->sets[c->pipeline ? (c->passSeq & 1) : 0];
+        Counters *dc = static_cast<Counters *>(ss.counters.ptr);
         g.indices = devIndices + first * per;
         g.numPrims = (int)n;
         g.firstBatch = (uint32_t)(first / kBatch);
+        g.bbox = static_cast<Box16 *>(ss.bbox.ptr);
+        g.gbox = static_cast<Box16 *>(ss.gbox.ptr);
+        g.head = static_cast<float4 *>(ss.head.ptr);
+        g.params = static_cast<float *>(ss.params.ptr);
+        g.span = static_cast<float4 *>(ss.span.ptr);
+        g.tilemap = static_cast<uint32_t *>(ss.tilemap.ptr);
+        g.extra = static_cast<uint2 *>(ss.extra.ptr);
+        g.extraAlloc = &dc->extraAlloc;
+        g.errorFlag = &dc->errorFlag;
+        t.bbox = g.bbox; t.gbox = g.gbox; t.head = g.head; t.params = g.params; t.span = g.span;
+        t.tilemap = g.tilemap;
+        t.extra = g.extra;
+        t.fragCounter = &dc->fragments;
+        t.errorFlag = &dc->errorFlag;
         t.numPrims = (int)n;
         t.numChunks = (int)(2 * ((n + kBatch - 1) / kBatch));
-        CUDA_TRY(cudaMemsetAsync(c->tilemap.ptr, 0, (size_t)tilesX * tilesY * chunkWords * 4, c->stream));
-        CUDA_TRY(cudaMemcpyAsync(&dc->extraAlloc, &extrasBegin, sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-        if (c->debugStream) CUDA_TRY(cudaMemsetAsync(c->dbgVerts.ptr, 0xff, recCap * 48, c->stream));
-        geomLaunch(&g, c->stream);
-        if (first + passPrims >= nprims) CUDA_TRY(cudaEventRecord(c->evGeom1, c->stream));
+
+        // geometry stream: wait until the tile kernel that last read this set is done, then refill it
+        if (gs != c->stream && ss.tilePending) CUDA_TRY(cudaStreamWaitEvent(gs, ss.tileDone, 0));
+        CUDA_TRY(cudaMemsetAsync(ss.tilemap.ptr, 0, (size_t)tilesX * tilesY * chunkWords * 4, gs));
+        const uint32_t init[2] = { extrasBegin, 0u };                    // extraAlloc, errorFlag
+        CUDA_TRY(cudaMemcpyAsync(&dc->extraAlloc, init, sizeof(init), cudaMemcpyHostToDevice, gs));
+        if (c->debugStream) CUDA_TRY(cudaMemsetAsync(c->dbgVerts.ptr, 0xff, recCap * 48, gs));
+        geomLaunch(&g, gs);
+        if (first + passPrims >= nprims) CUDA_TRY(cudaEventRecord(c->evGeom1, gs));
+        // main stream: tiles of this pass after its geometry
+        if (gs != c->stream) {
+            CUDA_TRY(cudaEventRecord(ss.geomDone, gs));
+            CUDA_TRY(cudaStreamWaitEvent(c->stream, ss.geomDone, 0));
+        }
+        if (firstPass) CUDA_TRY(cudaEventRecord(c->evTile0, c->stream));
+        firstPass = false;
         tileLaunch(&t, c->stream);
+        if (gs != c->stream) {
+            CUDA_TRY(cudaEventRecord(ss.tileDone, c->stream));
+            ss.tilePending = true;
+        }
         c->stats.kernel_launches += 2;
         c->stats.passes++;
         c->lastPassPrims = (int)n;
         c->lastFirstBatch = g.firstBatch;
+        c->lastSet = (int)(&ss - c->sets);
+        c->passSeq++;
     }
     CUDA_TRY(cudaEventRecord(c->evTile1, c->stream));
     CUDA_TRY(cudaGetLastError());
@@ -467,10 +530,15 @@ int swr_create(swr_context **out, int cuda_device)
     c->device = cuda_device;
     cudaError_t e = cudaSetDevice(cuda_device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->ownStream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking);
     c->stream = c->ownStream;
-    cudaEvent_t *evs[] = { &c->evGeom0, &c->evGeom1, &c->evTile1, &c->evTimer0, &c->evTimer1 };
+    cudaEvent_t *evs[] = { &c->evGeom0, &c->evGeom1, &c->evTile0, &c->evTile1, &c->evTimer0, &c->evTimer1 };
     for (cudaEvent_t *ev : evs)
         if (e == cudaSuccess) e = cudaEventCreate(ev);
+    cudaEvent_t *sync[] = { &c->evDrawStart, &c->sets[0].geomDone, &c->sets[0].tileDone, &c->sets[1].geomDone, &c->sets[1].tileDone };
+    for (cudaEvent_t *ev : sync)
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
+    if (const char *env = getenv("SWR_PIPELINE")) c->pipeline = atoi(env) != 0;
     if (e != cudaSuccess) {
         delete c;
         return fail(-22, "context creation: %s", cudaGetErrorString(e));
@@ -488,15 +556,18 @@ void swr_destroy(swr_context *c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
+    if (c->aux) cudaStreamSynchronize(c->aux);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    DevBuf *bufs[] = { &c->bbox, &c->gbox, &c->head, &c->params, &c->span, &c->tilemap, &c->extra, &c->counters,
-                       &c->dbgVerts, &c->stageIdx, &c->l2flush, &c->ownedIdx, &c->tileStats };
+    DevBuf *bufs[] = { &c->dbgVerts, &c->stageIdx, &c->l2flush, &c->ownedIdx, &c->tileStats };
     for (DevBuf *b : bufs) b->release();
+    for (ScratchSet &ss : c->sets) ss.release();
     for (int i = 0; i < SWR_MAX_VERTEX_ATTRIBS; ++i) c->stageAttrib[i].release();
     if (c->hostFlags) cudaFreeHost(c->hostFlags);
-    cudaEvent_t evs[] = { c->evGeom0, c->evGeom1, c->evTile1, c->evTimer0, c->evTimer1 };
+    cudaEvent_t evs[] = { c->evGeom0, c->evGeom1, c->evTile0, c->evTile1, c->evTimer0, c->evTimer1, c->evDrawStart,
+                          c->sets[0].geomDone, c->sets[0].tileDone, c->sets[1].geomDone, c->sets[1].tileDone };
     for (cudaEvent_t ev : evs)
         if (ev) cudaEventDestroy(ev);
+    if (c->aux) cudaStreamDestroy(c->aux);
     if (c->ownStream) cudaStreamDestroy(c->ownStream);
     delete c;
 }
@@ -614,8 +685,23 @@ int swr_set_stream(swr_context *c, void *cuda_stream)
 {
     if (!c) return fail(-1, "null context");
     if (int rc = setDevice(c)) return rc;
+    CUDA_TRY(cudaStreamSynchronize(c->aux));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
+    for (ScratchSet &ss : c->sets) ss.tilePending = false;
     c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->ownStream;
+    return 0;
+}
+
+int swr_set_pipeline(swr_context *c, int enable, int passes_hint, int overlap_draws)
+{
+    if (!c) return fail(-1, "null context");
+    if (int rc = setDevice(c)) return rc;
+    CUDA_TRY(cudaStreamSynchronize(c->aux));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    for (ScratchSet &ss : c->sets) ss.tilePending = false;
+    c->pipeline = enable != 0;
+    c->passesHint = passes_hint;
+    c->overlapDraws = enable != 0 && overlap_draws != 0;
     return 0;
 }
 
@@ -645,15 +731,19 @@ int swr_finish(swr_context *c)
 {
     if (!c) return fail(-1, "null context");
     if (int rc = setDevice(c)) return rc;
-    if (c->countersInit) {
-        Counters *dc = static_cast<Counters *>(c->counters.ptr);
-        CUDA_TRY(cudaMemcpyAsync(c->hostFlags, &dc->stickyFlag, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->aux));
+    for (int k = 0; k < 2; ++k) {
+        ScratchSet &ss = c->sets[k];
+        if (!ss.countersInit) continue;
+        Counters *dc = static_cast<Counters *>(ss.counters.ptr);
+        CUDA_TRY(cudaMemcpyAsync(c->hostFlags + k, &dc->stickyFlag, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(cudaMemsetAsync(&dc->stickyFlag, 0, sizeof(uint32_t), c->stream));
     }
     CUDA_TRY(cudaStreamSynchronize(c->stream));
-    if (c->hostFlags && c->hostFlags[0]) {
-        const uint32_t f = c->hostFlags[0];
-        c->hostFlags[0] = 0;
+    for (ScratchSet &ss : c->sets) ss.tilePending = false;
+    if (c->hostFlags && (c->hostFlags[0] | c->hostFlags[1])) {
+        const uint32_t f = c->hostFlags[0] | c->hostFlags[1];
+        c->hostFlags[0] = c->hostFlags[1] = 0;
         if (f & 1u) return fail(-30, "geometry scratch exhausted: the last draw produced nothing (raise swr_set_scratch_limit)");
         if (f & 2u) return fail(-31, "a line longer than %d DDA steps was dropped", kMaxLineSteps);
     }
@@ -664,15 +754,20 @@ int swr_get_stats(swr_context *c, swr_stats *out)
 {
     if (!c || !out) return fail(-1, "null argument");
     if (int rc = setDevice(c)) return rc;
+    CUDA_TRY(cudaStreamSynchronize(c->aux));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
-    if (c->counters.ptr) {
-        Counters h;
-        CUDA_TRY(cudaMemcpy(&h, c->counters.ptr, sizeof(h), cudaMemcpyDeviceToHost));
-        c->stats.fragments = h.fragments;
-    }
+    c->stats.fragments = 0;
+    for (ScratchSet &ss : c->sets)
+        if (ss.countersInit) {
+            Counters h;
+            CUDA_TRY(cudaMemcpy(&h, ss.counters.ptr, sizeof(h), cudaMemcpyDeviceToHost));
+            c->stats.fragments += h.fragments;
+        }
     if (c->haveDrawEvents) {
+        // geometry: first launch to last completion on its stream; tiles: first launch to the end of the
+        // draw on the main stream.  With pipelining on, the two intervals overlap.
         cudaEventElapsedTime(&c->stats.last_geometry_ms, c->evGeom0, c->evGeom1);
-        cudaEventElapsedTime(&c->stats.last_tile_ms, c->evGeom1, c->evTile1);
+        cudaEventElapsedTime(&c->stats.last_tile_ms, c->evTile0, c->evTile1);
     }
     c->stats.scratch_bytes = scratchBytes(c);
     *out = c->stats;
@@ -683,8 +778,10 @@ int swr_reset_stats(swr_context *c)
 {
     if (!c) return fail(-1, "null context");
     if (int rc = setDevice(c)) return rc;
+    CUDA_TRY(cudaStreamSynchronize(c->aux));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
-    if (c->counters.ptr) CUDA_TRY(cudaMemset(&static_cast<Counters *>(c->counters.ptr)->fragments, 0, sizeof(unsigned long long)));
+    for (ScratchSet &ss : c->sets)
+        if (ss.countersInit) CUDA_TRY(cudaMemset(&static_cast<Counters *>(ss.counters.ptr)->fragments, 0, sizeof(unsigned long long)));
     const uint64_t scratch = c->stats.scratch_bytes;
     const int tile = c->stats.last_tile_size;
     memset(&c->stats, 0, sizeof(c->stats));
@@ -727,6 +824,7 @@ int swr_device_free(swr_context *c, void *ptr)
 {
     if (!c) return fail(-1, "null context");
     if (int rc = setDevice(c)) return rc;
+    CUDA_TRY(cudaStreamSynchronize(c->aux));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     CUDA_TRY(cudaFree(ptr));
     return 0;
@@ -873,15 +971,17 @@ int64_t swr_debug_read_stream(swr_context *c, int16_t *bbox, uint32_t *ordinal, 
     if (int rc = setDevice(c)) return rc;
     if (cudaStreamSynchronize(c->stream) != cudaSuccess) return fail(-100, "sync failed");
     const int n = c->lastPassPrims;
-    if (n == 0 || !c->bbox.ptr) return 0;
+    const ScratchSet &ls = c->sets[c->lastSet];
+    cudaStreamSynchronize(c->aux);
+    if (n == 0 || !ls.bbox.ptr) return 0;
     const int batches = (n + kBatch - 1) / kBatch;
     std::vector<uint2> extra(batches);
-    if (cudaMemcpy(extra.data(), c->extra.ptr, sizeof(uint2) * batches, cudaMemcpyDeviceToHost) != cudaSuccess) return fail(-100, "copy failed");
+    if (cudaMemcpy(extra.data(), ls.extra.ptr, sizeof(uint2) * batches, cudaMemcpyDeviceToHost) != cudaSuccess) return fail(-100, "copy failed");
     size_t maxRec = (size_t)batches * kBatch;
     for (const uint2 &e : extra) maxRec = std::max(maxRec, (size_t)e.x + e.y);
     std::vector<Box16> hb(maxRec);
     std::vector<float> hv;
-    if (cudaMemcpy(hb.data(), c->bbox.ptr, sizeof(Box16) * maxRec, cudaMemcpyDeviceToHost) != cudaSuccess) return fail(-100, "copy failed");
+    if (cudaMemcpy(hb.data(), ls.bbox.ptr, sizeof(Box16) * maxRec, cudaMemcpyDeviceToHost) != cudaSuccess) return fail(-100, "copy failed");
     if (verts && c->dbgVerts.ptr) {
         hv.resize(maxRec * 12);
         if (cudaMemcpy(hv.data(), c->dbgVerts.ptr, sizeof(float) * 12 * maxRec, cudaMemcpyDeviceToHost) != cudaSuccess) return fail(-100, "copy failed");

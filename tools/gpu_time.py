@@ -42,6 +42,20 @@ def timed(scene, tile, reps=5, check=False):
         ms = sr.r.timerEnd()
         st = sr.r.stats()
         ts.append((ms, st.last_geometry_ms, st.last_tile_ms, st.fragments))
+    # K back-to-back draws (throughput), optionally with the next draw's geometry under this draw's tiles
+    for overlap in (0, 1):
+        sr.r.setPipeline(True, 0, bool(overlap))
+        for _ in range(2):
+            sr.draw(scene, vertices=vb, indices=ib, wait=False)
+        sr.r.finish()
+        K = 10
+        sr.r.timerBegin()
+        for _ in range(K):
+            sr.draw(scene, vertices=vb, indices=ib, wait=False)
+        ms = sr.r.timerEnd()
+        sr.r.finish()
+        print(f"   back-to-back x{K} overlap_draws={overlap}: {ms / K:.3f} ms/draw", flush=True)
+    sr.r.setPipeline(False, 0, False)
     best = min(ts)
     print(f"TIME {scene.name:36s} tile{st.last_tile_size} prims {scene.num_primitives:>9d} frags {best[3]:>11d} total {best[0]:8.3f}ms geom {best[1]:7.3f} tile {best[2]:8.3f} "
           f"-> {scene.num_primitives / best[0] / 1e6:6.2f} Gprim/s {best[3] / best[0] / 1e6:7.2f} Gfrag/s", flush=True)

@@ -11,15 +11,15 @@
 
 namespace swr {
 
-/// Read-only array view over consecutive (a, b, c) planes.
+/// Read-only array view over consecutive planes stored as (a, b, c, 0).
 struct ParameterEquationArray {
     const float *planes;
     SWR_HD ParameterEquation operator[](int i) const
     {
         ParameterEquation p;
-        p.a = planes[3 * i + 0];
-        p.b = planes[3 * i + 1];
-        p.c = planes[3 * i + 2];
+        p.a = planes[4 * i + 0];
+        p.b = planes[4 * i + 1];
+        p.c = planes[4 * i + 2];
         return p;
     }
 };

@@ -6,7 +6,7 @@
 //                         (min > max  <=>  dead: clipped away, culled, zero area, off-screen)
 //   gbox   [R/32] 4 x int16 union of the 32 records of one group (one warp of the geometry kernel)
 //   head   [R]  3 x float4 edge equations / line start+step / point position, flags, ordinal
-//   params [R]  paramStride floats: interpolation planes (a,b,c) in the order z?, invw?, avar[], pvar[]
+//   params [R]  paramStride floats: interpolation planes, one float4 (a,b,c,0) each, in the order z?, invw?, avar[], pvar[]
 //               (lines: (start, step) pairs; points: values)
 //   span   [R]  3 x float4 (Span / Adaptive only) the two scan-converted halves
 //   tilemap[tile][chunk/32] one bit per (screen tile, chunk): chunk may touch the tile
@@ -149,7 +149,7 @@ SWR_HD int paramFloats(int drawMode, int nA, int nP, int useZ, int useW)
 {
     if (drawMode == SWR_DRAW_TRIANGLE) {
         int planes = (useZ ? 1 : 0) + ((useW || nP > 0) ? 1 : 0) + nA + nP;
-        return ((planes * 3) + 3) & ~3;
+        return planes * 4;                           // one float4 (a, b, c, 0) per plane: a single 128-bit access each
     }
     int vars = (useZ ? 1 : 0) + (useW ? 1 : 0) + nA + nP;
     int n = drawMode == SWR_DRAW_LINE ? vars * 2 : vars;

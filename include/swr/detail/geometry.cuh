@@ -313,32 +313,32 @@ SWR_HD Box16 emitScreenTriangle(const GeomArgs &g, uint32_t rec, uint32_t ordina
     hd[1] = mkf4(e1.b, e1.c, e2.a, e2.b);
     hd[2] = mkf4(e2.c, u2f(flags), u2f(ordinal), area2);
 
-    // interpolation planes (TriangleEquations.h:59-70), order: z?, invw?, avar[nA], pvar[nP]
-    float *pp = g.params + (size_t)rec * g.paramStride;
+    // interpolation planes (TriangleEquations.h:59-70), order: z?, invw?, avar[nA], pvar[nP]; one float4 each
+    float4 *pp4 = reinterpret_cast<float4 *>(g.params + (size_t)rec * g.paramStride);
     const float factor = fdiv(1.0f, area2);
     ParameterEquation pe;
     if (g.useZ) {
         pe.init(v0->z, v1->z, v2->z, e0, e1, e2, factor);
-        pp[0] = pe.a; pp[1] = pe.b; pp[2] = pe.c; pp += 3;
+        *pp4++ = mkf4(pe.a, pe.b, pe.c, 0.0f);
     }
     float iw0 = 0.0f, iw1 = 0.0f, iw2 = 0.0f;
     if (g.useW || g.nP > 0) {
         iw0 = fdiv(1.0f, v0->w); iw1 = fdiv(1.0f, v1->w); iw2 = fdiv(1.0f, v2->w);
         pe.init(iw0, iw1, iw2, e0, e1, e2, factor);
-        pp[0] = pe.a; pp[1] = pe.b; pp[2] = pe.c; pp += 3;
+        *pp4++ = mkf4(pe.a, pe.b, pe.c, 0.0f);
     }
 #pragma unroll
     for (int i = 0; i < NA; ++i) {
         if (i < g.nA) {
             pe.init(v0->a[i], v1->a[i], v2->a[i], e0, e1, e2, factor);
-            pp[0] = pe.a; pp[1] = pe.b; pp[2] = pe.c; pp += 3;
+            *pp4++ = mkf4(pe.a, pe.b, pe.c, 0.0f);
         }
     }
 #pragma unroll
     for (int i = 0; i < NP; ++i) {
         if (i < g.nP) {
             pe.init(fmul(v0->p[i], iw0), fmul(v1->p[i], iw1), fmul(v2->p[i], iw2), e0, e1, e2, factor);
-            pp[0] = pe.a; pp[1] = pe.b; pp[2] = pe.c; pp += 3;
+            *pp4++ = mkf4(pe.a, pe.b, pe.c, 0.0f);
         }
     }
     return box;

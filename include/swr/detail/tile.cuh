@@ -391,26 +391,32 @@ SWR_HD void shadeTriangleFragment(const TileArgs &t, uint32_t rec, int gx, int g
         return v;
     };
 
+    // one 128-bit load per plane
+    const float4 *pl4 = reinterpret_cast<const float4 *>(pl);
     int o = 0;
     if (TR::Z) {
-        eq.z.a = pl[0]; eq.z.b = pl[1]; eq.z.c = pl[2];
-        p.z = chain(eq.z.a, eq.z.b, eq.z.c);
-        o += 3;
+        const float4 q = pl4[o++];
+        eq.z.a = q.x; eq.z.b = q.y; eq.z.c = q.z;
+        p.z = chain(q.x, q.y, q.z);
     }
     if (TR::WP) {
-        eq.invw.a = pl[o]; eq.invw.b = pl[o + 1]; eq.invw.c = pl[o + 2];
-        p.invw = chain(eq.invw.a, eq.invw.b, eq.invw.c);
+        const float4 q = pl4[o++];
+        eq.invw.a = q.x; eq.invw.b = q.y; eq.invw.c = q.z;
+        p.invw = chain(q.x, q.y, q.z);
         p.w = fdiv(1.0f, p.invw);
-        o += 3;
     }
-    eq.avar.planes = pl + o;
+    eq.avar.planes = pl + 4 * o;
 #pragma unroll
-    for (int i = 0; i < TR::NA; ++i) p.avar[i] = chain(pl[o + 3 * i], pl[o + 3 * i + 1], pl[o + 3 * i + 2]);
-    o += 3 * TR::NA;
-    eq.pvar.planes = pl + o;
+    for (int i = 0; i < TR::NA; ++i) {
+        const float4 q = pl4[o + i];
+        p.avar[i] = chain(q.x, q.y, q.z);
+    }
+    o += TR::NA;
+    eq.pvar.planes = pl + 4 * o;
 #pragma unroll
     for (int i = 0; i < TR::NP; ++i) {
-        p.pvarTemp[i] = chain(pl[o + 3 * i], pl[o + 3 * i + 1], pl[o + 3 * i + 2]);
+        const float4 q = pl4[o + i];
+        p.pvarTemp[i] = chain(q.x, q.y, q.z);
         p.pvar[i] = fmul(p.pvarTemp[i], p.w);
     }
     p.equations = &eq;

@@ -49,6 +49,22 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(workload: str, tile: int, world: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the tile kernel from the committed ncu --set full capture
+    (profiles/r01_summary.json: C3, 64-pixel tiles, one GPU); None for any other configuration."""
+    if workload != "c3" or tile != 64 or world != 1:
+        return None
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r01_summary.json")))["tile"]
+
+        def mb(v):
+            num, unit = v.split()[:2]
+            return float(num) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[unit]
+        return mb(d["dram__bytes_read.sum"]) + mb(d["dram__bytes_write.sum"])
+    except Exception:
+        return None
+
+
 def make_scene(name: str):
     if name == "c3":
         return S.config_c3(), 4, "BASELINE.json configs[2]: 10M tiny-triangle mesh, 3840x2160, Block, Gouraud, CullMode::CW"
@@ -342,7 +358,8 @@ def run_gpu_arm(args):
                              if scene.indices.nbytes + scene.vertices.nbytes > 126e6 else "inputs fit in L2 (no flush between steps)",
                        "clear": "render targets cleared once before timing (the Gouraud shader overwrites)"},
             "roofline": {"bound": "hbm", "kernel": "tileKernel (binning + coverage + shading of one screen tile per CTA)",
-                         "achieved": ach_tile, "peak": peak, "unit": "GB/s", "frac": ach_tile / peak, "traffic": None,
+                         "achieved": ach_tile, "peak": peak, "unit": "GB/s", "frac": ach_tile / peak,
+                         "traffic": ncu_traffic(args.workload, tile, world),
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": frag_b / world,
                          "kernel_ms": t_tile * 1e3, "geometry_kernel_ms": t_geom * 1e3,
                          "draw": {"algorithmic_bytes": geom_b + frag_b / world, "achieved": ach_draw, "frac": ach_draw / peak,

@@ -50,16 +50,23 @@ enum { SWR_RASTER_SPAN = 0, SWR_RASTER_BLOCK = 1, SWR_RASTER_ADAPTIVE = 2 };    
 /* ---- stock shader pack (compiled into libswr_b200.so; ids shared with oracle/swr_scene.h) - */
 enum { SWR_VS_POS_COLOR = 0, SWR_VS_MVP_COLOR = 1, SWR_VS_MVP_NORMAL_UV = 2, SWR_VS_COUNT = 3 };
 enum { SWR_PS_FLAT = 0, SWR_PS_COUNT_ID = 1, SWR_PS_GOURAUD = 2, SWR_PS_GOURAUD_DEPTH = 3,
-       SWR_PS_VARY_DUMP = 4, SWR_PS_TEXTURED = 5, SWR_PS_COUNT = 6 };
+       SWR_PS_VARY_DUMP = 4, SWR_PS_TEXTURED = 5, SWR_PS_TEXTURED_ANISO = 6, SWR_PS_COUNT = 7 };
 
 /* Render-target slots used by the stock pixel shaders. */
 enum { SWR_RT_COLOR = 0, SWR_RT_DEPTH = 1, SWR_RT_COUNT = 2, SWR_RT_PRIM_ID = 3, SWR_RT_VARY0 = 4 /* ..11 */ };
 
 /* Uniform block read by the stock shaders (swr_set_uniforms). */
+#define SWR_MAX_MIP_LEVELS 14
 typedef struct swr_stock_uniforms {
     float mvp[16];               /* row-major: clip.x = m[0]*x + m[1]*y + m[2]*z + m[3]*w */
-    const uint32_t *texture;     /* device pointer, tex_w * tex_h texels */
+    const uint32_t *texture;     /* device pointer, tex_w * tex_h texels (0x00RRGGBB) */
     int32_t tex_w, tex_h;        /* powers of two */
+    /* mip chain for SWR_PS_TEXTURED_ANISO (same layout as swr::TextureView, include/swr/Texture.h) */
+    const uint32_t *mip[SWR_MAX_MIP_LEVELS];
+    int32_t mip_w[SWR_MAX_MIP_LEVELS];
+    int32_t mip_h[SWR_MAX_MIP_LEVELS];
+    int32_t mip_levels;
+    int32_t max_anisotropy;
 } swr_stock_uniforms;
 
 /* ---- shader programs ------------------------------------------------------------------------ */

@@ -16,6 +16,8 @@
 #include "Renderer.h"      // reference: src/renderer/Renderer.h
 #include "Random.h"        // reference: src/examples/Random.h
 #include "vector_math.h"   // reference: src/examples/vector_math.h
+#include "SDL.h"           // oracle/sdl_shim/SDL.h (stand-in for the SDL2 names Texture.h uses)
+#include "Texture.h"       // reference: src/examples/Texture.h, unmodified
 
 #include <cmath>
 #include <cstring>
@@ -168,6 +170,26 @@ struct PSTextured : public PixelShaderBase<PSTextured> {
     }
 };
 
+// Box.cpp:39-62: perspective-correct UV derivatives + the reference's anisotropic / trilinear sampler.
+Texture *g_texture = nullptr;
+
+struct PSTexturedAniso : public PixelShaderBase<PSTexturedAniso> {
+    static const bool InterpolateZ = false;
+    static const bool InterpolateW = true;
+    static const int AVarCount = 0;
+    static const int PVarCount = 2;
+    static void drawPixel(const PixelData &p)
+    {
+        g_s->fragments++;
+        float dudx, dudy, dvdx, dvdy;
+        p.computePerspectiveDerivatives(*p.equations, 0, dudx, dudy);
+        p.computePerspectiveDerivatives(*p.equations, 1, dvdx, dvdy);
+        Uint32 sampledColor;
+        g_texture->sample(p.pvar[0], p.pvar[1], dudx, dvdx, dudy, dvdy, sampledColor);
+        g_s->color[p.x + g_s->width * p.y] = sampledColor;
+    }
+};
+
 // ---------------------------------------------------------------- recording rasterizer
 // Forwards primitive by primitive to the reference Rasterizer (same loops as
 // Rasterizer.h:116-141) and stamps the emission ordinal first.
@@ -274,6 +296,15 @@ int ref_draw(swr_scene *s)
     case SWR_PS_GOURAUD_DEPTH: drawWithPS<PSGouraudDepth>(r, v, s); break;
     case SWR_PS_VARY_DUMP: drawWithPS<PSVaryDump>(r, v, s); break;
     case SWR_PS_TEXTURED: drawWithPS<PSTextured>(r, v, s); break;
+    case SWR_PS_TEXTURED_ANISO: {
+        if (s->draw_mode != 2 || !s->texture) return -5;       // Box.cpp's shader dereferences p.equations
+        SDL_Surface base = { s->tex_w, s->tex_h, s->tex_w * 4, const_cast<uint32_t *>(s->texture) };
+        Texture tex(&base);                                    // builds the mip chain (Texture.h:220-293)
+        g_texture = &tex;
+        drawWithPS<PSTexturedAniso>(r, v, s);
+        g_texture = nullptr;
+        break;
+    }
     default: return -2;
     }
     g_s = nullptr;

@@ -44,6 +44,8 @@ typedef struct {                /* TriangleEquations.h:35-45 */
     plane_eq z, invw, avar[MAX_AVARS], pvar[MAX_PVARS];
 } tri_eq;
 
+static float plane_eval_fwd(const plane_eq *p, float x, float y) { return p->a * x + p->b * y + p->c; }
+
 typedef struct {                /* PixelData.h:38-58 (what drawPixel may read) */
     int x, y;
     float z, w, invw;
@@ -61,6 +63,10 @@ typedef struct {
     float px, py, ox, oy;       /* VertexProcessor.cpp:50-53 */
     int minX, minY, maxX, maxY; /* Rasterizer.h:81-87 (max exclusive) */
     uint32_t ordinal;
+    const tri_eq *cur_eq;       /* PixelData::equations of the fragment being shaded */
+    /* mip chain of the textured_aniso shader (Texture.h:220-293) */
+    uint32_t *mip[16];
+    int mip_w[16], mip_h[16], mip_levels, max_aniso;
 } ctx;
 
 /* ------------------------------------------------------------------ stock shaders */
@@ -103,6 +109,141 @@ static uint32_t pack_rgb(const frag *p)  /* RasterizerTest.cpp:39-45 */
     return (uint32_t)(r << 16 | g << 8 | b);
 }
 
+/* ------------------------------------------------------------------ Texture.h restated */
+static int tex_r(uint32_t c) { return (int)((c >> 16) & 0xFF); }
+static int tex_g(uint32_t c) { return (int)((c >> 8) & 0xFF); }
+static int tex_b(uint32_t c) { return (int)(c & 0xFF); }
+static uint32_t tex_pack(int r, int g, int b) { return ((uint32_t)(r & 0xFF) << 16) | ((uint32_t)(g & 0xFF) << 8) | (uint32_t)(b & 0xFF); }
+static int tex_u8(float v) { return (int)v & 0xFF; }      /* (Uint8)float the way x86 code does it */
+
+/* Texture.h:220-293: 2x2 box filter down to 1x1 */
+static int tex_build_mips(ctx *c, const uint32_t *base, int w, int h)
+{
+    c->mip_levels = 0;
+    uint32_t *lv = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)w * (size_t)h);
+    if (!lv) return -4;
+    memcpy(lv, base, sizeof(uint32_t) * (size_t)w * (size_t)h);
+    c->mip[0] = lv; c->mip_w[0] = w; c->mip_h[0] = h; c->mip_levels = 1;
+    while ((w > 1 || h > 1) && c->mip_levels < 16) {
+        int nw = w / 2 > 1 ? w / 2 : 1, nh = h / 2 > 1 ? h / 2 : 1;
+        const uint32_t *src = c->mip[c->mip_levels - 1];
+        uint32_t *dst = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)nw * (size_t)nh);
+        if (!dst) return -4;
+        for (int y = 0; y < nh; y++)
+            for (int x = 0; x < nw; x++) {
+                uint32_t p00 = src[(y * 2) * w + (x * 2)];
+                uint32_t p10 = x * 2 + 1 < w ? src[(y * 2) * w + (x * 2 + 1)] : p00;
+                uint32_t p01 = y * 2 + 1 < h ? src[(y * 2 + 1) * w + (x * 2)] : p00;
+                uint32_t p11 = (x * 2 + 1 < w && y * 2 + 1 < h) ? src[(y * 2 + 1) * w + (x * 2 + 1)] : p00;
+                dst[y * nw + x] = tex_pack((tex_r(p00) + tex_r(p10) + tex_r(p01) + tex_r(p11)) >> 2,
+                                           (tex_g(p00) + tex_g(p10) + tex_g(p01) + tex_g(p11)) >> 2,
+                                           (tex_b(p00) + tex_b(p10) + tex_b(p01) + tex_b(p11)) >> 2);
+            }
+        c->mip[c->mip_levels] = dst; c->mip_w[c->mip_levels] = nw; c->mip_h[c->mip_levels] = nh;
+        c->mip_levels++;
+        w = nw; h = nh;
+    }
+    return 0;
+}
+
+static void tex_free_mips(ctx *c)
+{
+    for (int i = 0; i < c->mip_levels; ++i) free(c->mip[i]);
+    c->mip_levels = 0;
+}
+
+static uint32_t tex_lerp(uint32_t c1, uint32_t c2, float t)  /* Texture.h:191-196 */
+{
+    return tex_pack(tex_r(c1) + tex_u8((tex_r(c2) - tex_r(c1)) * t),
+                    tex_g(c1) + tex_u8((tex_g(c2) - tex_g(c1)) * t),
+                    tex_b(c1) + tex_u8((tex_b(c2) - tex_b(c1)) * t));
+}
+
+static int tex_bilerp_channel(int c00, int c10, int c01, int c11, float fx, float fy)  /* Texture.h:199-204 */
+{
+    return tex_u8(c00 * (1 - fx) * (1 - fy) + c10 * fx * (1 - fy) + c01 * (1 - fx) * fy + c11 * fx * fy);
+}
+
+static uint32_t tex_bilinear(const ctx *c, int mip, float u, float v)  /* Texture.h:145-180 */
+{
+    if (mip < 0 || mip >= c->mip_levels) return 0;
+    int w = c->mip_w[mip], h = c->mip_h[mip];
+    const uint32_t *px = c->mip[mip];
+    float fpx = u * (w - 1), fpy = v * (h - 1);
+    int x0 = (int)floorf(fpx); if (x0 < 0) x0 = 0;
+    int y0 = (int)floorf(fpy); if (y0 < 0) y0 = 0;
+    int x1 = x0 + 1 < w - 1 ? x0 + 1 : w - 1;
+    int y1 = y0 + 1 < h - 1 ? y0 + 1 : h - 1;
+    float fx = fpx - x0, fy = fpy - y0;
+    uint32_t c00 = px[y0 * w + x0], c10 = px[y0 * w + x1], c01 = px[y1 * w + x0], c11 = px[y1 * w + x1];
+    return tex_pack(tex_bilerp_channel(tex_r(c00), tex_r(c10), tex_r(c01), tex_r(c11), fx, fy),
+                    tex_bilerp_channel(tex_g(c00), tex_g(c10), tex_g(c01), tex_g(c11), fx, fy),
+                    tex_bilerp_channel(tex_b(c00), tex_b(c10), tex_b(c01), tex_b(c11), fx, fy));
+}
+
+static uint32_t tex_trilinear(const ctx *c, float u, float v, float rho)  /* Texture.h:123-143 */
+{
+    float lod = log2f(rho > 1e-6f ? rho : 1e-6f);
+    float top = (float)(c->mip_levels - 1);
+    lod = lod < 0.0f ? 0.0f : (top < lod ? top : lod);
+    int lodBase = (int)floorf(lod);
+    int lodNext = lodBase + 1 < c->mip_levels - 1 ? lodBase + 1 : c->mip_levels - 1;
+    float lodFrac = lod - lodBase;
+    lodFrac = lodFrac < 0.0f ? 0.0f : (1.0f < lodFrac ? 1.0f : lodFrac);
+    uint32_t cb = tex_bilinear(c, lodBase, u, v);
+    if (lodBase != lodNext) return tex_lerp(cb, tex_bilinear(c, lodNext, u, v), lodFrac);
+    return cb;
+}
+
+static float tex_wrap(float x) { x = fmodf(x, 1.0f); if (x < 0) x += 1.0f; return x; }  /* Texture.h:41-44 */
+
+static uint32_t tex_sample(const ctx *c, float u, float v, float dudx, float dvdx, float dudy, float dvdy)  /* Texture.h:35-118 */
+{
+    if (c->mip_levels <= 0) return 0;
+    u = tex_wrap(u);
+    v = tex_wrap(v);
+    float dudx_s = dudx * c->mip_w[0], dvdx_s = dvdx * c->mip_h[0];
+    float dudy_s = dudy * c->mip_w[0], dvdy_s = dvdy * c->mip_h[0];
+    float dx_len = sqrtf(dudx_s * dudx_s + dvdx_s * dvdx_s);
+    float dy_len = sqrtf(dudy_s * dudy_s + dvdy_s * dvdy_s);
+    dx_len = dx_len < 1e-6f ? 1e-6f : dx_len;
+    dy_len = dy_len < 1e-6f ? 1e-6f : dy_len;
+    float major_len = dx_len < dy_len ? dy_len : dx_len;
+    float minor_len = dy_len < dx_len ? dy_len : dx_len;
+    float ratio = major_len / minor_len;
+    ratio = (float)c->max_aniso < ratio ? (float)c->max_aniso : ratio;
+    int num = (int)ceilf(ratio);
+    if (num < 1) num = 1;
+    if (num <= 1) return tex_trilinear(c, u, v, major_len);
+    float mdu, mdv;
+    if (dx_len > dy_len) { mdu = dudx / dx_len; mdv = dvdx / dx_len; }
+    else { mdu = dudy / dy_len; mdv = dvdy / dy_len; }
+    float r = 0, g = 0, b = 0;
+    float step = 1.0f / num;
+    for (int i = 0; i < num; ++i) {
+        float t = (i + 0.5f) * step - 0.5f;
+        float su = tex_wrap(u + mdu * major_len * t);
+        float sv = tex_wrap(v + mdv * major_len * t);
+        uint32_t sc = tex_trilinear(c, su, sv, minor_len);
+        r += tex_r(sc); g += tex_g(sc); b += tex_b(sc);
+    }
+    r = r / num; r = 255.0f < r ? 255.0f : r;
+    g = g / num; g = 255.0f < g ? 255.0f : g;
+    b = b / num; b = 255.0f < b ? 255.0f : b;
+    return tex_pack(tex_u8(r), tex_u8(g), tex_u8(b));
+}
+
+/* PixelData::computePerspectiveDerivatives (PixelData.h:128-145) */
+static void persp_derivs(const tri_eq *q, int var, int x, int y, float *ddx, float *ddy)
+{
+    float val = plane_eval_fwd(&q->pvar[var], x + 0.5f, y + 0.5f);
+    float iw = plane_eval_fwd(&q->invw, x + 0.5f, y + 0.5f);
+    float dvar_dx = q->pvar[var].a, dvar_dy = q->pvar[var].b;
+    float dinvw_dx = q->invw.a, dinvw_dy = q->invw.b;
+    *ddx = (iw * dvar_dx - val * dinvw_dx) / (iw * iw);
+    *ddy = (iw * dvar_dy - val * dinvw_dy) / (iw * iw);
+}
+
 /* The stock drawPixel bodies (same as ref_driver.cpp / stock_shaders.cuh). */
 static void draw_pixel(ctx *c, const frag *p)
 {
@@ -138,10 +279,17 @@ static void draw_pixel(ctx *c, const frag *p)
         s->vary[7 * n + i] = p->pvar[1];
         s->count[i]++;
         break;
-    default: { /* SWR_PS_TEXTURED */
+    case SWR_PS_TEXTURED: {
         int tx = (int)floorf(p->pvar[0] * (float)s->tex_w) & (s->tex_w - 1);
         int ty = (int)floorf(p->pvar[1] * (float)s->tex_h) & (s->tex_h - 1);
         s->color[i] = s->texture[ty * s->tex_w + tx];
+        break;
+    }
+    default: { /* SWR_PS_TEXTURED_ANISO: Box.cpp:49-61 */
+        float dudx, dudy, dvdx, dvdy;
+        persp_derivs(c->cur_eq, 0, p->x, p->y, &dudx, &dudy);
+        persp_derivs(c->cur_eq, 1, p->x, p->y, &dvdx, &dvdy);
+        s->color[i] = tex_sample(c, p->pvar[0], p->pvar[1], dudx, dvdx, dudy, dvdy);
         break;
     }
     }
@@ -162,6 +310,7 @@ static int set_traits(int vs, int ps, traits *t)
     case SWR_PS_GOURAUD_DEPTH: t->nA = 3; t->useZ = 1; break;
     case SWR_PS_VARY_DUMP: t->nA = 3; t->nP = 2; t->useZ = 1; t->useW = 1; break;
     case SWR_PS_TEXTURED: t->nA = 3; t->nP = 2; t->useW = 1; break;
+    case SWR_PS_TEXTURED_ANISO: t->nP = 2; t->useW = 1; break;
     default: return -2;
     }
     return 0;
@@ -323,6 +472,7 @@ static void block_draw(ctx *c, const tri_eq *q, int x, int y, int test_edges)
     const traits *t = &c->t;
     float xf = x + 0.5f, yf = y + 0.5f;
     frag row;
+    c->cur_eq = q;
     float er[3] = { 0, 0, 0 };
     frag_init(&row, q, xf, yf, t);
     if (test_edges)
@@ -401,6 +551,7 @@ static void span_draw(ctx *c, const tri_eq *q, int x, int y, int x2)
 {
     frag p;
     p.y = y;
+    c->cur_eq = q;
     frag_init(&p, q, x + 0.5f, y + 0.5f, &c->t);
     while (x < x2) {
         p.x = x;
@@ -685,6 +836,11 @@ static int ctx_init(ctx *c, swr_scene *s)
     s->fragments = 0;
     s->primitives_out = 0;
     s->stream_len = 0;
+    if (s->ps_kind == SWR_PS_TEXTURED_ANISO) {
+        if (s->draw_mode != 2 || !s->texture) return -5;    /* Box.cpp's shader dereferences p.equations */
+        c->max_aniso = 8;                                   /* Texture.h:14 default */
+        return tex_build_mips(c, s->texture, s->tex_w, s->tex_h);
+    }
     return 0;
 }
 
@@ -740,6 +896,7 @@ int oracle_draw(swr_scene *s)
         for (int64_t k = 0; k < nextra; ++k) rasterize(&c, &extras[k]);
     }
     free(extras);
+    tex_free_mips(&c);
     return 0;
 }
 

@@ -40,7 +40,8 @@ enum {
     SWR_PS_GOURAUD = 2,       /* A=3: color[i] = r<<16|g<<8|b                    (RasterizerTest.cpp:37-47) */
     SWR_PS_GOURAUD_DEPTH = 3, /* Z, A=3: if (z < depth[i]) { depth[i]=z; color[i]=rgb; }                   */
     SWR_PS_VARY_DUMP = 4,     /* Z, W, A=3, P=2: vary[k][i] = z,w,invw,a0,a1,a2,p0,p1; count[i]++           */
-    SWR_PS_TEXTURED = 5       /* W, A=3, P=2: color[i] = texture[nearest(u,v) wrapped]     (Box.cpp:39-62) */
+    SWR_PS_TEXTURED = 5,      /* W, A=3, P=2: color[i] = texture[nearest(u,v) wrapped]                     */
+    SWR_PS_TEXTURED_ANISO = 6 /* W, P=2: Box.cpp:39-62 verbatim: perspective derivatives + Texture::sample  */
 };
 #endif
 

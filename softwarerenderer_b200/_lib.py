@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(HERE, "libswr_b200" + os.environ.get("SWR_LIB_VARIANT", 
 
 MAX_RENDER_TARGETS = 12
 MAX_UNIFORM_BYTES = 1024
+MAX_MIP_LEVELS = 14
 
 
 class SwrStats(C.Structure):
@@ -24,7 +25,9 @@ class SwrStats(C.Structure):
 
 class StockUniforms(C.Structure):
     """struct swr_stock_uniforms (include/swr_b200.h)."""
-    _fields_ = [("mvp", C.c_float * 16), ("texture", C.c_void_p), ("tex_w", C.c_int32), ("tex_h", C.c_int32)]
+    _fields_ = [("mvp", C.c_float * 16), ("texture", C.c_void_p), ("tex_w", C.c_int32), ("tex_h", C.c_int32),
+                ("mip", C.c_void_p * MAX_MIP_LEVELS), ("mip_w", C.c_int32 * MAX_MIP_LEVELS), ("mip_h", C.c_int32 * MAX_MIP_LEVELS),
+                ("mip_levels", C.c_int32), ("max_anisotropy", C.c_int32)]
 
 
 # every symbol include/swr_b200.h declares: (name, restype, argtypes)

@@ -32,7 +32,7 @@ class RasterMode:    # Rasterizer.h:45-49
 
 
 VS_NAMES = {"pos_color": 0, "mvp_color": 1, "mvp_normal_uv": 2}
-PS_NAMES = {"flat": 0, "count_id": 1, "gouraud": 2, "gouraud_depth": 3, "vary_dump": 4, "textured": 5}
+PS_NAMES = {"flat": 0, "count_id": 1, "gouraud": 2, "gouraud_depth": 3, "vary_dump": 4, "textured": 5, "textured_aniso": 6}
 RT_COLOR, RT_DEPTH, RT_COUNT, RT_PRIM_ID, RT_VARY0 = 0, 1, 2, 3, 4
 VARY_PLANES = 8
 
@@ -300,13 +300,24 @@ class SceneRenderer:
             tex = np.ascontiguousarray(scene.texture, dtype=np.uint32)
             key = (tex.ctypes.data, tex.shape)
             if self._tex_key != key:
+                from .scenes import build_mip_chain
                 if self._tex:
                     self.r.free(self._tex)
-                self._tex = self.r.alloc(tex.nbytes)
-                self.r.upload(self._tex, tex)
+                self._mips = build_mip_chain(tex)                     # level 0 = the texture itself
+                chain = np.concatenate([m.reshape(-1) for m in self._mips])
+                chain[:tex.size] = tex.reshape(-1)                    # nearest-fetch shader reads the raw texels
+                self._tex = self.r.alloc(chain.nbytes)
+                self.r.upload(self._tex, chain)
                 self._tex_key = key
             u.texture = self._tex
             u.tex_h, u.tex_w = tex.shape
+            off = 0
+            for i, m in enumerate(self._mips[:_lib.MAX_MIP_LEVELS]):
+                u.mip[i] = self._tex + off * 4
+                u.mip_h[i], u.mip_w[i] = m.shape
+                off += m.size
+            u.mip_levels = min(len(self._mips), _lib.MAX_MIP_LEVELS)
+            u.max_anisotropy = 8                                      # Texture.h:14 default
         return u
 
     def set_state(self, scene):

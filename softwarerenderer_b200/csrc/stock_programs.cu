@@ -1,7 +1,7 @@
 // stock_programs.cu -- instantiates the geometry / tile kernels for the stock shader pack.
 //
 // Built once per unit (-DSWR_STOCK_UNIT=n, see Makefile) so the heavy tile-kernel instantiations
-// compile in parallel: unit 0 = the vertex shaders, units 1..6 = one pixel shader each.  Every
+// compile in parallel: unit 0 = the vertex shaders, units 1..7 = one pixel shader each.  Every
 // unit is its own translation unit and therefore has its own uniform block (swr/Uniforms.h).
 #include "stock_shaders.cuh"
 
@@ -28,6 +28,7 @@ extern "C" const swr_pixel_shader *swr_stock_ps_gouraud(void);
 extern "C" const swr_pixel_shader *swr_stock_ps_gouraud_depth(void);
 extern "C" const swr_pixel_shader *swr_stock_ps_vary_dump(void);
 extern "C" const swr_pixel_shader *swr_stock_ps_textured(void);
+extern "C" const swr_pixel_shader *swr_stock_ps_textured_aniso(void);
 
 extern "C" SWR_API const swr_pixel_shader *swr_stock_pixel_shader(int ps_kind)
 {
@@ -38,6 +39,7 @@ extern "C" SWR_API const swr_pixel_shader *swr_stock_pixel_shader(int ps_kind)
     case SWR_PS_GOURAUD_DEPTH: return swr_stock_ps_gouraud_depth();
     case SWR_PS_VARY_DUMP: return swr_stock_ps_vary_dump();
     case SWR_PS_TEXTURED: return swr_stock_ps_textured();
+    case SWR_PS_TEXTURED_ANISO: return swr_stock_ps_textured_aniso();
     default: return nullptr;
     }
 }
@@ -53,4 +55,6 @@ extern "C" const swr_pixel_shader *swr_stock_ps_gouraud_depth(void) { return pix
 extern "C" const swr_pixel_shader *swr_stock_ps_vary_dump(void) { return pixelShaderBinding<stock::PSVaryDump>("vary_dump"); }
 #elif SWR_STOCK_UNIT == 6
 extern "C" const swr_pixel_shader *swr_stock_ps_textured(void) { return pixelShaderBinding<stock::PSTextured>("textured"); }
+#elif SWR_STOCK_UNIT == 7
+extern "C" const swr_pixel_shader *swr_stock_ps_textured_aniso(void) { return pixelShaderBinding<stock::PSTexturedAniso>("textured_aniso"); }
 #endif

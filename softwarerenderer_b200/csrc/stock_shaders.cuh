@@ -8,10 +8,12 @@
 // -fmad=false so that the shader bodies round like the oracle's (-ffp-contract=off).
 #pragma once
 
+#include <cstddef>
 #include <swr/VertexShaderBase.h>
 #include <swr/PixelShaderBase.h>
 #include <swr/detail/geometry.cuh>
 #include <swr/detail/tile.cuh>
+#include <swr/Texture.h>
 
 namespace stock {
 
@@ -142,6 +144,27 @@ struct PSTextured : public PixelShaderBase<PSTextured> {       // Box.cpp:39-62,
         int tx = (int)floorf(p.pvar[0] * (float)u.tex_w) & (u.tex_w - 1);
         int ty = (int)floorf(p.pvar[1] * (float)u.tex_h) & (u.tex_h - 1);
         target<unsigned>(p, SWR_RT_COLOR) = __ldg(u.texture + ty * u.tex_w + tx);
+    }
+};
+
+static_assert(SWR_MAX_MIP_LEVELS == swr::kMaxMipLevels, "uniform block and TextureView disagree");
+static_assert(offsetof(swr_stock_uniforms, max_anisotropy) - offsetof(swr_stock_uniforms, mip) == offsetof(swr::TextureView, maxAnisotropy),
+              "swr_stock_uniforms::mip.. must have the layout of swr::TextureView");
+
+struct PSTexturedAniso : public PixelShaderBase<PSTexturedAniso> {   // Box.cpp:39-62, verbatim structure
+    static const bool InterpolateZ = false;
+    static const bool InterpolateW = true;  // Required for perspective correct texturing
+    static const int AVarCount = 0;
+    static const int PVarCount = 2;         // UV coordinates
+    static const int RenderTargets = 1;
+    __device__ static void drawPixel(const PixelData &p)
+    {
+        // Compute texture coordinate derivatives
+        float dudx, dudy, dvdx, dvdy;
+        p.computePerspectiveDerivatives(*p.equations, 0, dudx, dudy); // U derivatives
+        p.computePerspectiveDerivatives(*p.equations, 1, dvdx, dvdy); // V derivatives
+        const TextureView &tex = *reinterpret_cast<const TextureView *>(&uniforms<swr_stock_uniforms>().mip[0]);
+        target<unsigned>(p, SWR_RT_COLOR) = textureSample(tex, p.pvar[0], p.pvar[1], dudx, dvdx, dudy, dvdy);
     }
 };
 

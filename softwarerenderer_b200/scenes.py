@@ -26,7 +26,7 @@ RASTER_SPAN, RASTER_BLOCK, RASTER_ADAPTIVE = 0, 1, 2
 
 # Stock shader ids (include/swr_b200.h, oracle/swr_scene.h).
 VS_POS_COLOR, VS_MVP_COLOR, VS_MVP_NORMAL_UV = 0, 1, 2
-PS_FLAT, PS_COUNT_ID, PS_GOURAUD, PS_GOURAUD_DEPTH, PS_VARY_DUMP, PS_TEXTURED = 0, 1, 2, 3, 4, 5
+PS_FLAT, PS_COUNT_ID, PS_GOURAUD, PS_GOURAUD_DEPTH, PS_VARY_DUMP, PS_TEXTURED, PS_TEXTURED_ANISO = 0, 1, 2, 3, 4, 5, 6
 
 ORDINAL_STRIDE = 10240
 VARY_PLANES = 8
@@ -256,6 +256,30 @@ def checker_texture(size: int = 256, seed: int = 7) -> np.ndarray:
     yy, xx = np.meshgrid(np.arange(size), np.arange(size), indexing="ij")
     check = (((xx >> 4) ^ (yy >> 4)) & 1).astype(np.uint32)
     return (base & np.uint32(0x003F3F3F)) | (check * np.uint32(0x00C0C0C0))
+
+
+def build_mip_chain(base: np.ndarray):
+    """Texture::generateMipmaps (Texture.h:220-293): 2x2 box filter per channel with >> 2, down to 1x1.
+    Returns the list of uint32 [h, w] levels (level 0 = base)."""
+    lv = (np.ascontiguousarray(base, dtype=np.uint32) & np.uint32(0x00FFFFFF))
+    levels = [lv]
+    while lv.shape[0] > 1 or lv.shape[1] > 1:
+        h, w = lv.shape
+        nh, nw = max(1, h // 2), max(1, w // 2)
+        ys, xs = np.arange(nh) * 2, np.arange(nw) * 2
+        y1 = np.where(ys + 1 < h, ys + 1, -1)
+        x1 = np.where(xs + 1 < w, xs + 1, -1)
+        p00 = lv[np.ix_(ys, xs)]
+        p10 = np.where((x1 >= 0)[None, :], lv[np.ix_(ys, np.maximum(x1, 0))], p00)
+        p01 = np.where((y1 >= 0)[:, None], lv[np.ix_(np.maximum(y1, 0), xs)], p00)
+        p11 = np.where((y1 >= 0)[:, None] & (x1 >= 0)[None, :], lv[np.ix_(np.maximum(y1, 0), np.maximum(x1, 0))], p00)
+        out = np.zeros((nh, nw), dtype=np.uint32)
+        for shift in (16, 8, 0):
+            ch = sum(((p >> np.uint32(shift)) & np.uint32(0xFF)).astype(np.uint32) for p in (p00, p10, p01, p11)) >> np.uint32(2)
+            out |= (ch & np.uint32(0xFF)) << np.uint32(shift)
+        levels.append(out)
+        lv = out
+    return levels
 
 
 # --------------------------------------------------------------------------- configs

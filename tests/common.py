@@ -60,6 +60,11 @@ def parity_scenes(ntri=2048, small=True):
     out.append(("c3_small_id", S.config_c3(250, 200, 480, 270, ps=S.PS_COUNT_ID)))
     out.append(("c4_lines_small", S.config_c4(100, 50, 480, 270)))
     out.append(("c4_points_small", S.config_c4(100, 50, 480, 270, draw_mode=S.DRAW_POINT)))
+    # Box.cpp's own pixel shader: perspective derivatives + the reference's Texture::sample (Texture.h)
+    for th, m in ((0.0, m0), (0.5, m05), (2.0, m2)):
+        out.append((f"box_th{th}_aniso_span", S.config_c1(bv, bi, tex, th, raster_mode=S.RASTER_SPAN, ps=S.PS_TEXTURED_ANISO, mvp=m)))
+    out.append(("boxnear_aniso_block", S.config_c1(bv, bi, tex, 0, raster_mode=S.RASTER_BLOCK, ps=S.PS_TEXTURED_ANISO, mvp=mnear).replace(cull_mode=S.CULL_NONE)))
+    out.append(("c5_small_aniso", S.config_c5(100, 80, 3, 480, 270, ps=S.PS_TEXTURED_ANISO)))
     out.append(("c5_small", S.config_c5(100, 80, 3, 480, 270)))
     out.append(("c5_small_vary", S.config_c5(100, 80, 3, 480, 270, ps=S.PS_VARY_DUMP)))
     return out
@@ -73,6 +78,15 @@ def diff_buffers(got, want, keys=BUFFERS):
         if d:
             bad[k] = d
     return bad
+
+
+def max_channel_diff(a, b):
+    """Largest per-channel difference between two 0x00RRGGBB buffers, and how many pixels differ."""
+    a, b = a.astype(np.int64), b.astype(np.int64)
+    d = 0
+    for sh in (16, 8, 0):
+        d = np.maximum(d, np.abs(((a >> sh) & 255) - ((b >> sh) & 255)))
+    return int(d.max()), int((d > 0).sum())
 
 
 def known_answers():

@@ -18,6 +18,7 @@
 #include <swr/PixelShaderBase.h>
 #include <swr/detail/geometry.cuh>
 #include <swr/detail/tile.cuh>
+#include <swr/Texture.h>
 
 #include "../../oracle/swr_scene.h"
 
@@ -112,6 +113,21 @@ struct HPSVaryDump : PixelShaderBase<HPSVaryDump> {
         v[3 * n + i] = p.avar[0]; v[4 * n + i] = p.avar[1]; v[5 * n + i] = p.avar[2];
         v[6 * n + i] = p.pvar[0]; v[7 * n + i] = p.pvar[1];
         g_s->count[i]++;
+    }
+};
+
+TextureView g_tex;
+
+struct HPSTexturedAniso : PixelShaderBase<HPSTexturedAniso> {
+    static const bool InterpolateW = true;
+    static const int PVarCount = 2;
+    static void drawPixel(const PixelData &p)
+    {
+        g_s->fragments++;
+        float dudx, dudy, dvdx, dvdy;
+        p.computePerspectiveDerivatives(*p.equations, 0, dudx, dudy);
+        p.computePerspectiveDerivatives(*p.equations, 1, dvdx, dvdy);
+        g_s->color[p.x + g_s->width * p.y] = textureSample(g_tex, p.pvar[0], p.pvar[1], dudx, dvdx, dudy, dvdy);
     }
 };
 
@@ -287,6 +303,16 @@ extern "C" int hostcheck_draw(swr_scene *s)
     case SWR_PS_GOURAUD: return runVS<HPSGouraud>(s);
     case SWR_PS_GOURAUD_DEPTH: return runVS<HPSGouraudDepth>(s);
     case SWR_PS_VARY_DUMP: return runVS<HPSVaryDump>(s);
+    case 6: {   // SWR_PS_TEXTURED_ANISO
+        if (s->draw_mode != 2 || !s->texture) return -5;
+        std::vector<uint32_t> chain((size_t)s->tex_w * s->tex_h * 2 + 16);
+        int32_t w[kMaxMipLevels], h[kMaxMipLevels];
+        int64_t off[kMaxMipLevels];
+        g_tex.levels = buildMipChain(s->texture, s->tex_w, s->tex_h, chain.data(), w, h, off);
+        for (int i = 0; i < g_tex.levels; ++i) { g_tex.level[i] = chain.data() + off[i]; g_tex.w[i] = w[i]; g_tex.h[i] = h[i]; }
+        g_tex.maxAnisotropy = 8;
+        return runVS<HPSTexturedAniso>(s);
+    }
     default: return -2;
     }
 }

@@ -15,12 +15,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SRC = os.path.join(HERE, "hostcheck", "hostcheck.cu")
 SO = os.path.join(HERE, "hostcheck", "libhostcheck.so")
-SUPPORTED_PS = (S.PS_COUNT_ID, S.PS_GOURAUD, S.PS_GOURAUD_DEPTH, S.PS_VARY_DUMP)
+SUPPORTED_PS = (S.PS_COUNT_ID, S.PS_GOURAUD, S.PS_GOURAUD_DEPTH, S.PS_VARY_DUMP, S.PS_TEXTURED_ANISO)
 
 
 @pytest.fixture(scope="module")
 def hostcheck(oracle):
-    deps = [SRC] + [os.path.join(ROOT, "include", "swr", "detail", f) for f in ("common.h", "geometry.cuh", "tile.cuh")]
+    deps = [SRC, os.path.join(ROOT, "include", "swr", "Texture.h")] + [os.path.join(ROOT, "include", "swr", "detail", f) for f in ("common.h", "geometry.cuh", "tile.cuh")]
     if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
         subprocess.run(["/usr/local/cuda/bin/nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17",
                         "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared", "-I" + os.path.join(ROOT, "include"),

@@ -15,6 +15,11 @@ def box_mesh():
     return d["vertices"], d["indices"], d["mvp_theta0"], d["mvp_theta05"], d["mvp_theta2"], d["mvp_near"]
 
 
+def box_texture():
+    """data/box.png as 0x00RRGGBB words (fixture made by tests/golden/make_golden.py)."""
+    return np.load(os.path.join(GOLDEN, "box_texture.npz"))["texture"].astype(np.uint32)
+
+
 def heavy_clip_mvp():
     """v*3 - 1.5 on x, y, z as a matrix (heavy 6-plane clipping)."""
     m = np.eye(4, dtype=np.float32)
@@ -64,6 +69,8 @@ def parity_scenes(ntri=2048, small=True):
     for th, m in ((0.0, m0), (0.5, m05), (2.0, m2)):
         out.append((f"box_th{th}_aniso_span", S.config_c1(bv, bi, tex, th, raster_mode=S.RASTER_SPAN, ps=S.PS_TEXTURED_ANISO, mvp=m)))
     out.append(("boxnear_aniso_block", S.config_c1(bv, bi, tex, 0, raster_mode=S.RASTER_BLOCK, ps=S.PS_TEXTURED_ANISO, mvp=mnear).replace(cull_mode=S.CULL_NONE)))
+    # BASELINE.json configs[0] as the reference ships it: box.obj + box.png, 640x480, Span, Box.cpp's shaders
+    out.append(("c1_box_png_aniso_span", S.config_c1(bv, bi, box_texture(), 0.5, raster_mode=S.RASTER_SPAN, ps=S.PS_TEXTURED_ANISO, mvp=m05)))
     out.append(("c5_small_aniso", S.config_c5(100, 80, 3, 480, 270, ps=S.PS_TEXTURED_ANISO)))
     out.append(("c5_small", S.config_c5(100, 80, 3, 480, 270)))
     out.append(("c5_small_vary", S.config_c5(100, 80, 3, 480, 270, ps=S.PS_VARY_DUMP)))

@@ -3,6 +3,7 @@
 Run in the development container only (it needs /root/reference):
     python tests/golden/make_golden.py
 Outputs (committed):
+    box_texture.npz     data/box.png decoded to 0x00RRGGBB words
     box_mesh.npz        data/box.obj through our OBJ loader + the Box.cpp cameras computed by the
                         reference's own vector_math.h (ref_box_mvp)
     random0_prefix.npy  first 256 values of the reference's Random(0).NextDouble()
@@ -52,6 +53,10 @@ def main():
              mvp_theta0=O.ref_box_mvp(eye(0.0)), mvp_theta05=O.ref_box_mvp(eye(0.5)), mvp_theta2=O.ref_box_mvp(eye(2.0)),
              mvp_near=O.ref_box_mvp((1.2, 0.3, 0.4)))
     np.save(os.path.join(HERE, "random0_prefix.npy"), O.ref_random_doubles(0, 256))
+    # data/box.png decoded to the 0x00RRGGBB words Texture.h expects (alpha is 255 everywhere)
+    from PIL import Image
+    rgba = np.asarray(Image.open("/root/reference/data/box.png").convert("RGBA"), dtype=np.uint32)
+    np.savez_compressed(os.path.join(HERE, "box_texture.npz"), texture=(rgba[..., 0] << 16) | (rgba[..., 1] << 8) | rgba[..., 2])
 
     import common  # tests/common.py (needs box_mesh.npz)
     answers = {}

@@ -71,7 +71,7 @@ SWR_HD int ffs32(uint32_t v)
 #endif
 }
 
-struct Box16 { int16_t x0, y0, x1, y1; };        // inclusive; dead when x0 > x1
+struct alignas(8) Box16 { int16_t x0, y0, x1, y1; };        // inclusive; dead when x0 > x1
 SWR_HD Box16 deadBox() { Box16 b; b.x0 = 32767; b.y0 = 32767; b.x1 = -32768; b.y1 = -32768; return b; }
 
 // head flags
@@ -141,7 +141,7 @@ struct TileArgs {
     int32_t scMinX, scMinY, scMaxX, scMaxY;
     unsigned long long *fragCounter;
     const uint32_t *errorFlag;
-    uint32_t *tileStats;             // optional debug: 8 words per tile {globaltimer ns start, ns duration, primitives, fragments, A0/A/B clocks >> 4 of thread 0, 0}
+    uint32_t *tileStats;             // optional debug: 16 words per tile {globaltimer ns start, ns duration, primitives, fragments, A0/A/B clocks >> 4 of thread 0, flushes, flush prologue / F3 / F1+F2 clocks >> 4, records tested, groups tested, 0...}
 };
 
 // number of floats of one params record

@@ -51,7 +51,7 @@ namespace detail {
 constexpr int kQueue = SWR_QUEUE;    // primitives per flush
 constexpr int kItems = SWR_ITEMS;    // (primitive, block) items per flush
 constexpr int kChunkList = 1024;
-constexpr int kGroupList = 1024;
+constexpr int kGroupList = 4096;
 constexpr int kTileWarps = kTileThreads / 32;
 constexpr int kPruneMax = 16;        // primitives with at most this many (primitive, block) items get the emptiness pre-test
 static_assert(2 * kTileThreads >= kQueue, "the item re-indexing scan handles two queue entries per thread");
@@ -79,10 +79,12 @@ struct TileSmem {
 
 struct Ctl { uint32_t accQ, accItems; int nextBlock; };
 
-// Exclusive block scan of a packed (hi: count, lo: sum) pair.  Two barriers; scratch is double
-// buffered so back-to-back calls need no trailing barrier.
+// Exclusive block scan of a packed (hi: count, lo: sum) pair.  ONE barrier: every warp publishes its
+// total, then each warp scans the (at most 32) warp totals for itself.  The scratch is double buffered,
+// so back-to-back calls need no trailing barrier (a warp can be at most one call behind the others).
 SWR_D uint64_t blockScan(uint64_t v, uint64_t &total, uint64_t *scratch, int &phase)
 {
+    static_assert(kTileWarps <= 32, "one lane per warp total");
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint64_t *s = scratch + phase * (kTileWarps + 1);
     phase ^= 1;
@@ -94,21 +96,24 @@ SWR_D uint64_t blockScan(uint64_t v, uint64_t &total, uint64_t *scratch, int &ph
     }
     if (lane == 31) s[wid] = incl;
     __syncthreads();
-    if (wid == 0) {
-        uint64_t w = lane < kTileWarps ? s[lane] : 0;
-        uint64_t wi = w;
+    const uint64_t w = lane < kTileWarps ? s[lane] : 0;
+    uint64_t wi = w;
 #pragma unroll
-        for (int o = 1; o < kTileWarps; o <<= 1) {
-            uint64_t n = __shfl_up_sync(0xffffffffu, wi, o);
-            if (lane >= o) wi += n;
-        }
-        if (lane < kTileWarps) s[lane] = wi - w;
-        if (lane == kTileWarps - 1) s[kTileWarps] = wi;
+    for (int o = 1; o < kTileWarps; o <<= 1) {
+        uint64_t n = __shfl_up_sync(0xffffffffu, wi, o);
+        if (lane >= o) wi += n;
     }
-    __syncthreads();
-    total = s[kTileWarps];
-    return incl - v + s[wid];
+    total = __shfl_sync(0xffffffffu, wi, kTileWarps - 1);
+    return incl - v + __shfl_sync(0xffffffffu, wi - w, wid);
 }
+
+#ifndef SWR_PREFETCH
+#define SWR_PREFETCH 7
+#endif
+#ifndef SWR_TILE_STATS
+#define SWR_TILE_STATS 0          // per-tile / per-phase clocks (tools/tile_stats.py builds its own library variant)
+#endif
+SWR_D void prefetchL2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 SWR_D bool boxOverlaps(const Box16 b, int X0, int Y0, int X1, int Y1)
 {
@@ -564,21 +569,24 @@ __global__ void __launch_bounds__(kTileThreads, SWR_TILE_MINB) tileKernel(const 
     unsigned long long frags = 0;
     unsigned long long tStart = 0;
     long long cycA0 = 0, cycA = 0, cycB = 0, cycMark = 0;      // debug: per-phase clocks of thread 0
+    long long cycPre = 0, cycF3 = 0, cycF12 = 0, cycIn = 0;
+    uint32_t dbgPairs = 0, dbgGroups = 0;
     uint32_t dbgFlush = 0;
-    const bool timing = t.tileStats != nullptr && tid == 0;
+    const bool timing = SWR_TILE_STATS && t.tileStats != nullptr && tid == 0;
     if (timing) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tStart));
 
     // ---- flush: coverage (A) + shading (B) of the queued primitives -----------------------------
     auto flushQueue = [&]() {
         if (nQ == 0) return;
         primsSeen += nQ;
-        if (timing) { cycMark = clock64(); ++dbgFlush; }
+        if (timing) { cycMark = clock64(); cycIn = cycMark; ++dbgFlush; }
         if (tid == 0) ctl->nextBlock = 0;
         for (int i = tid; i < NB * QW; i += kTileThreads) sBlockmap[i] = 0;
         if (!loaded) {
             moveTile<TLOG, TR::NRT, false>(t, rtSmem, X0, Y0);
             loaded = true;
         }
+        if (timing) { const long long c = clock64(); cycPre += c - cycMark; cycMark = c; }
 
         // A0: drop the (primitive, block) items whose block provably holds no covered pixel (about
         // half of them on tiny-triangle meshes: the reference visits every block of the truncated
@@ -653,6 +661,11 @@ __global__ void __launch_bounds__(kTileThreads, SWR_TILE_MINB) tileKernel(const 
                 m = ((unsigned)lx < 8u && (unsigned)ly < 8u) ? 1ull << (ly * 8 + lx) : 0ull;
             }
             sMasks[it] = m;
+            if ((SWR_PREFETCH & 2) && m) {
+                const char *pp = (const char *)(t.params + (size_t)rec * t.paramStride);
+                prefetchL2(pp);
+                prefetchL2(pp + t.paramStride * 4 - 4);
+            }
             if (m) atomicOr(&sBlockmap[(by * BPR + bx) * QW + (q >> 5)], 1u << (q & 31));
         }
         __syncthreads();
@@ -787,43 +800,73 @@ __global__ void __launch_bounds__(kTileThreads, SWR_TILE_MINB) tileKernel(const 
             }   // word chunks
         }
         __syncthreads();
-        if (timing) cycB += clock64() - cycMark;
+        if (timing) { const long long c = clock64(); cycB += c - cycMark; cycF3 -= c - cycIn; }
         nQ = 0;
         nItems = 0;
     };
 
     // ---- F3: records of the listed groups -> queue ------------------------------------------------
+    // Four consecutive records per thread and scan step (one 32-byte read of their boxes): a quarter of
+    // the barriers, four loads in flight per thread.
     auto drainGroups = [&]() {
         __syncthreads();                                     // gList writes of the caller are visible
         const uint32_t npairs = nGroup * 32u;
-        for (uint32_t pb = 0; pb < npairs; pb += kTileThreads) {
-            const uint32_t pr = pb + tid;
-            bool hit = false;
-            uint32_t rec = 0, range = 0, items = 0;
-            if (pr < npairs) {
-                rec = gList[pr >> 5] * 32u + (pr & 31u);
-                const Box16 bb = t.bbox[rec];
-                if (boxOverlaps(bb, X0, Y0, X1, Y1)) {
-                    hit = true;
-                    const int bx0 = (max((int)bb.x0, X0) - X0) >> 3, by0 = (max((int)bb.y0, Y0) - Y0) >> 3;
-                    const int bx1 = (min((int)bb.x1, X1) - X0) >> 3, by1 = (min((int)bb.y1, Y1) - Y0) >> 3;
-                    range = (uint32_t)bx0 | ((uint32_t)by0 << 8) | ((uint32_t)bx1 << 16) | ((uint32_t)by1 << 24);
-                    items = (uint32_t)((bx1 - bx0 + 1) * (by1 - by0 + 1));
-                }
+        const long long f3In = timing ? clock64() : 0;
+        if (SWR_TILE_STATS) dbgPairs += npairs;
+        for (uint32_t pb = 0; pb < npairs; pb += 4u * kTileThreads) {
+            const uint32_t pr0 = pb + 4u * tid;
+            uint32_t pend = 0, rec0 = 0;                     // bit k: record rec0 + k still has to be tested / queued
+            if (pr0 < npairs) {
+                rec0 = gList[pr0 >> 5] * 32u + (pr0 & 31u);
+                pend = 0xfu;
             }
             while (true) {
+                // (re)derive the block ranges of the pending records; after a flush this re-reads the
+                // boxes (L1 hits), so only `pend` and `rec0` live across flushQueue()
+                uint32_t range[4] = { 0, 0, 0, 0 }, items[4] = { 0, 0, 0, 0 };
+                uint32_t cnt = 0, sum = 0;
+                if (pend) {
+                    const uint4 *bp = reinterpret_cast<const uint4 *>(t.bbox + rec0);
+                    const uint4 b01 = bp[0], b23 = bp[1];
+                    const uint32_t w[8] = { b01.x, b01.y, b01.z, b01.w, b23.x, b23.y, b23.z, b23.w };
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        Box16 bb;
+                        bb.x0 = (int16_t)(w[2 * k] & 0xffffu); bb.y0 = (int16_t)(w[2 * k] >> 16);
+                        bb.x1 = (int16_t)(w[2 * k + 1] & 0xffffu); bb.y1 = (int16_t)(w[2 * k + 1] >> 16);
+                        if (((pend >> k) & 1u) && boxOverlaps(bb, X0, Y0, X1, Y1)) {
+                            const int bx0 = (max((int)bb.x0, X0) - X0) >> 3, by0 = (max((int)bb.y0, Y0) - Y0) >> 3;
+                            const int bx1 = (min((int)bb.x1, X1) - X0) >> 3, by1 = (min((int)bb.y1, Y1) - Y0) >> 3;
+                            range[k] = (uint32_t)bx0 | ((uint32_t)by0 << 8) | ((uint32_t)bx1 << 16) | ((uint32_t)by1 << 24);
+                            items[k] = (uint32_t)((bx1 - bx0 + 1) * (by1 - by0 + 1));
+                            ++cnt;
+                            sum += items[k];
+                        } else {
+                            pend &= ~(1u << k);
+                        }
+                    }
+                }
                 uint64_t total;
-                const uint64_t ex = blockScan(hit ? ((1ull << 32) | items) : 0ull, total, sScan, phase);
+                const uint64_t ex = blockScan(((uint64_t)cnt << 32) | sum, total, sScan, phase);
                 const uint32_t totHit = (uint32_t)(total >> 32), totItems = (uint32_t)total;
                 if (totHit == 0) break;
-                const uint32_t exHit = (uint32_t)(ex >> 32), exItems = (uint32_t)ex;
+                uint32_t eh = (uint32_t)(ex >> 32), ei = (uint32_t)ex;
                 const bool fitsAll = nQ + totHit <= kQueue && nItems + totItems <= kItems;
-                const bool acc = hit && nQ + exHit < kQueue && nItems + exItems + items <= kItems;
-                if (acc) {
-                    qRec[nQ + exHit] = rec;
-                    qRange[nQ + exHit] = range;
-                    qItem[nQ + exHit] = nItems + exItems;
-                    hit = false;
+                uint32_t nAcc = 0, accItems = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if ((pend >> k) & 1u) {
+                        if (nQ + eh < kQueue && nItems + ei + items[k] <= kItems) {
+                            qRec[nQ + eh] = rec0 + k;
+                            qRange[nQ + eh] = range[k];
+                            qItem[nQ + eh] = nItems + ei;
+                            pend &= ~(1u << k);
+                            ++nAcc;
+                            accItems += items[k];
+                        }
+                        ++eh;
+                        ei += items[k];
+                    }
                 }
                 if (fitsAll) {
                     nQ += totHit;
@@ -833,7 +876,7 @@ __global__ void __launch_bounds__(kTileThreads, SWR_TILE_MINB) tileKernel(const 
                 // queue full: count what was accepted, flush, retry the rest
                 if (tid == 0) { ctl->accQ = 0; ctl->accItems = 0; }
                 __syncthreads();
-                if (acc) { atomicAdd(&ctl->accQ, 1u); atomicAdd(&ctl->accItems, items); }
+                if (nAcc) { atomicAdd(&ctl->accQ, nAcc); atomicAdd(&ctl->accItems, accItems); }
                 __syncthreads();
                 nQ += ctl->accQ;
                 nItems += ctl->accItems;
@@ -843,10 +886,12 @@ __global__ void __launch_bounds__(kTileThreads, SWR_TILE_MINB) tileKernel(const 
         }
         __syncthreads();
         nGroup = 0;
+        if (timing) { const long long c = clock64(); cycF3 += c - f3In; cycF12 -= c - f3In; }
     };
 
     // ---- F1 + F2 ----------------------------------------------------------------------------------
     const uint32_t *row = t.tilemap + (size_t)blockIdx.x * t.chunkWords;
+    const long long f12In = timing ? clock64() : 0;
     for (int wb = 0; wb < t.chunkWords; wb += kTileThreads) {
         uint32_t pending = (wb + tid < t.chunkWords) ? row[wb + tid] : 0u;
         while (true) {
@@ -885,25 +930,41 @@ __global__ void __launch_bounds__(kTileThreads, SWR_TILE_MINB) tileKernel(const 
             __syncthreads();
             const uint32_t nChunk = min(totChunks, (uint32_t)kChunkList);
             const uint32_t npairs = cPair[nChunk];
+            if (SWR_TILE_STATS) dbgGroups += npairs;
 
-            // F2: group boxes of the listed chunks -> group list
-            for (uint32_t pb = 0; pb < npairs; pb += kTileThreads) {
-                if (nGroup + kTileThreads > kGroupList) drainGroups();
-                const uint32_t pr = pb + tid;
-                bool hit = false;
-                uint32_t grp = 0;
-                if (pr < npairs) {
-                    uint32_t lo = 0, hi = nChunk;            // largest chunk entry with cPair[entry] <= pr
+            // F2: group boxes of the listed chunks -> group list (four consecutive groups per thread and scan step)
+            for (uint32_t pb = 0; pb < npairs; pb += 4u * kTileThreads) {
+                if (nGroup + 4u * kTileThreads > kGroupList) drainGroups();
+                const uint32_t pr0 = pb + 4u * tid;
+                uint32_t grp[4] = { 0, 0, 0, 0 }, hits = 0;
+                if (pr0 < npairs) {
+                    uint32_t lo = 0, hi = nChunk;            // largest chunk entry with cPair[entry] <= pr0
                     while (hi - lo > 1) {
                         const uint32_t mid = (lo + hi) >> 1;
-                        if (cPair[mid] <= pr) lo = mid; else hi = mid;
+                        if (cPair[mid] <= pr0) lo = mid; else hi = mid;
                     }
-                    grp = cGroup[lo] + (pr - cPair[lo]);
-                    hit = boxOverlaps(t.gbox[grp], X0, Y0, X1, Y1);
+                    uint32_t first = cPair[lo], next = cPair[lo + 1];
+                    Box16 gb[4];
+                    uint32_t valid = 0;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t pr = pr0 + k;
+                        if (pr < npairs) {
+                            while (pr >= next) { ++lo; first = next; next = cPair[lo + 1]; }
+                            grp[k] = cGroup[lo] + (pr - first);
+                            gb[k] = t.gbox[grp[k]];
+                            valid |= 1u << k;
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (((valid >> k) & 1u) && boxOverlaps(gb[k], X0, Y0, X1, Y1)) hits |= 1u << k;
                 }
                 uint64_t tot2;
-                const uint64_t ex2 = blockScan(hit ? 1ull : 0ull, tot2, sScan, phase);
-                if (hit) gList[nGroup + (uint32_t)ex2] = grp;
+                uint32_t e2 = nGroup + (uint32_t)blockScan((uint64_t)__popc(hits), tot2, sScan, phase);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if ((hits >> k) & 1u) gList[e2++] = grp[k];
                 nGroup += (uint32_t)tot2;
             }
             __syncthreads();
@@ -911,25 +972,33 @@ __global__ void __launch_bounds__(kTileThreads, SWR_TILE_MINB) tileKernel(const 
         }
     }
     drainGroups();
+    if (timing) cycF12 += clock64() - f12In;
+    const long long tailIn = timing ? clock64() : 0;
     flushQueue();
+    if (timing) cycF3 += clock64() - tailIn;     // flushQueue subtracted its own time from cycF3
 
     if (loaded) moveTile<TLOG, TR::NRT, true>(t, rtSmem, X0, Y0);
 
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) frags += __shfl_xor_sync(0xffffffffu, frags, o);
     if (lane == 0 && frags) atomicAdd(t.fragCounter, frags);
-    if (t.tileStats) {
-        if (lane == 0 && frags) atomicAdd(&t.tileStats[blockIdx.x * 8 + 3], (uint32_t)frags);
+    if (SWR_TILE_STATS && t.tileStats) {
+        if (lane == 0 && frags) atomicAdd(&t.tileStats[blockIdx.x * 16 + 3], (uint32_t)frags);
         if (tid == 0) {
             unsigned long long tEnd;
             asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tEnd));
-            t.tileStats[blockIdx.x * 8 + 0] = (uint32_t)tStart;
-            t.tileStats[blockIdx.x * 8 + 1] = (uint32_t)(tEnd - tStart);
-            t.tileStats[blockIdx.x * 8 + 2] = primsSeen;
-            t.tileStats[blockIdx.x * 8 + 4] = (uint32_t)(cycA0 >> 4);
-            t.tileStats[blockIdx.x * 8 + 5] = (uint32_t)(cycA >> 4);
-            t.tileStats[blockIdx.x * 8 + 6] = (uint32_t)(cycB >> 4);
-            t.tileStats[blockIdx.x * 8 + 7] = dbgFlush;
+            t.tileStats[blockIdx.x * 16 + 0] = (uint32_t)tStart;
+            t.tileStats[blockIdx.x * 16 + 1] = (uint32_t)(tEnd - tStart);
+            t.tileStats[blockIdx.x * 16 + 2] = primsSeen;
+            t.tileStats[blockIdx.x * 16 + 4] = (uint32_t)(cycA0 >> 4);
+            t.tileStats[blockIdx.x * 16 + 5] = (uint32_t)(cycA >> 4);
+            t.tileStats[blockIdx.x * 16 + 6] = (uint32_t)(cycB >> 4);
+            t.tileStats[blockIdx.x * 16 + 7] = dbgFlush;
+            t.tileStats[blockIdx.x * 16 + 8] = (uint32_t)(cycPre >> 4);
+            t.tileStats[blockIdx.x * 16 + 9] = (uint32_t)(cycF3 >> 4);
+            t.tileStats[blockIdx.x * 16 + 10] = (uint32_t)(cycF12 >> 4);
+            t.tileStats[blockIdx.x * 16 + 11] = dbgPairs;
+            t.tileStats[blockIdx.x * 16 + 12] = dbgGroups;
         }
     }
 }

@@ -188,9 +188,11 @@ SWR_API int64_t swr_owned_tile_count(int width, int height, int tile_size, int r
 /* Copies the geometry stage's records of the last pass to host arrays (any may be NULL):
  * bbox: 4 x int16 per record, ordinal: uint32 per record, verts: 12 floats (3 x xyzw screen space). */
 SWR_API int swr_debug_enable_stream(swr_context *ctx, int enable);
-/* Per-tile timing of the next draws: after a draw, swr_debug_read_tile_stats copies 8 uint32 per tile
+/* Per-tile timing of the next draws: after a draw, swr_debug_read_tile_stats copies 16 uint32 per tile
  * {start ns (low 32 bits of %globaltimer), duration ns, primitives queued, fragments, clocks/16 of thread 0 in the
- * pre-test / coverage / shading phases, 0}; returns the tile count. */
+ * pre-test / coverage / shading phases, flushes, clocks/16 in the flush prologue / record binning / chunk + group
+ * binning, records tested, groups tested, 0, 0, 0}; returns the tile count.  Only in builds with
+ * -DSWR_TILE_STATS=1 (the clocks cost ~2 %); the stock build returns an error from the enable call. */
 SWR_API int swr_debug_enable_tile_stats(swr_context *ctx, int enable);
 SWR_API int64_t swr_debug_read_tile_stats(swr_context *ctx, uint32_t *out, int64_t cap_tiles);
 SWR_API int64_t swr_debug_read_stream(swr_context *ctx, int16_t *bbox, uint32_t *ordinal, float *verts, int64_t cap);

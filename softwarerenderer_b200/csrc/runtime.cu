@@ -437,8 +437,8 @@ int drawCommon(swr_context *c, int drawMode, size_t count, const int32_t *indice
     for (int s = 0; s < SWR_MAX_RENDER_TARGETS; ++s) t.rt[s] = c->rt[s];
     t.scMinX = c->scMinX; t.scMinY = c->scMinY; t.scMaxX = c->scMaxX; t.scMaxY = c->scMaxY;
     if (c->debugTileStats) {
-        if (int rc = c->tileStats.reserve((size_t)tilesX * tilesY * 32)) return rc;
-        CUDA_TRY(cudaMemsetAsync(c->tileStats.ptr, 0, (size_t)tilesX * tilesY * 32, c->stream));
+        if (int rc = c->tileStats.reserve((size_t)tilesX * tilesY * 64)) return rc;
+        CUDA_TRY(cudaMemsetAsync(c->tileStats.ptr, 0, (size_t)tilesX * tilesY * 64, c->stream));
         t.tileStats = static_cast<uint32_t *>(c->tileStats.ptr);
         c->lastTiles = tilesX * tilesY;
     }
@@ -942,8 +942,13 @@ int swr_unpack_tiles(swr_context *c, int slot, int rank, int world, int tile_siz
 int swr_debug_enable_tile_stats(swr_context *c, int enable)
 {
     if (!c) return fail(-1, "null context");
+#if defined(SWR_TILE_STATS) && SWR_TILE_STATS
     c->debugTileStats = enable != 0;
     return 0;
+#else
+    (void)enable;
+    return fail(-7, "per-tile statistics are compiled out of this build (make VARIANT=_stats EXTRA=-DSWR_TILE_STATS=1)");
+#endif
 }
 
 int64_t swr_debug_read_tile_stats(swr_context *c, uint32_t *out, int64_t cap_tiles)
@@ -953,7 +958,7 @@ int64_t swr_debug_read_tile_stats(swr_context *c, uint32_t *out, int64_t cap_til
     if (cudaStreamSynchronize(c->stream) != cudaSuccess) return fail(-100, "sync failed");
     if (!c->tileStats.ptr) return 0;
     const int64_t n = std::min<int64_t>(cap_tiles, c->lastTiles);
-    if (cudaMemcpy(out, c->tileStats.ptr, (size_t)n * 32, cudaMemcpyDeviceToHost) != cudaSuccess) return fail(-100, "copy failed");
+    if (cudaMemcpy(out, c->tileStats.ptr, (size_t)n * 64, cudaMemcpyDeviceToHost) != cudaSuccess) return fail(-100, "copy failed");
     return c->lastTiles;
 }
 

@@ -5,6 +5,8 @@ import sys
 
 import numpy as np
 
+os.environ.setdefault("SWR_LIB_VARIANT", "_stats")   # make -C softwarerenderer_b200/csrc VARIANT=_stats EXTRA=-DSWR_TILE_STATS=1
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tools"))
@@ -26,7 +28,7 @@ sr.draw(scene, vertices=vb, indices=ib)
 st = sr.r.stats()
 T = st.last_tile_size
 tx, ty = (scene.width + T - 1) // T, (scene.height + T - 1) // T
-buf = np.zeros((tx * ty, 8), dtype=np.uint32)
+buf = np.zeros((tx * ty, 16), dtype=np.uint32)
 n = lib.swr_debug_read_tile_stats(sr.r.ctx, buf.ctypes.data, tx * ty)
 start, dur, prims, frags = [buf[:, i].astype(np.int64) for i in range(4)]
 cA0, cA, cB = [buf[:, i].astype(np.int64) * 16 / 1.965e3 for i in (4, 5, 6)]   # us at 1965 MHz
@@ -38,12 +40,15 @@ print(f"  sum of durations {dur.sum() / 1e6:.2f} ms -> / (148 SMs x 3 CTAs) = {d
 print(f"  prims per tile: mean {prims.mean():.0f} max {prims.max()};  frags per tile: mean {frags.mean():.0f} max {frags.max()}")
 print(f"  thread-0 phase time summed over tiles (ms): pre-test {cA0.sum() / 1e3:.1f}  coverage {cA.sum() / 1e3:.1f}  shading {cB.sum() / 1e3:.1f}  "
       f"binning+rest {(dur.sum() / 1e3 - cA0.sum() - cA.sum() - cB.sum()) / 1e3:.1f}  (total {dur.sum() / 1e6:.1f})")
+cPre, cF3, cF12 = [buf[:, i].astype(np.int32).astype(np.int64) * 16 / 1.965e3 for i in (8, 9, 10)]
+print(f"  of binning+rest (ms): flush prologue {cPre.sum() / 1e3:.1f}  F3 records {cF3.sum() / 1e3:.1f}  F1+F2 chunks/groups {cF12.sum() / 1e3:.1f};  "
+      f"records tested {buf[:, 11].astype(np.int64).sum()}  groups tested {buf[:, 12].astype(np.int64).sum()}  queued {prims.sum()}")
 w7 = buf[:, 7].astype(np.int64)
 nfl = w7
 print(f"  flushes {nfl.sum()}")
 order = np.argsort(-dur)[:12]
 for i in order:
-    print(f"    tile ({i % tx},{i // tx}) start +{rel[i] / 1e3:8.1f} us dur {dur[i] / 1e3:8.1f} us prims {prims[i]:7d} frags {frags[i]:7d}  A0 {cA0[i]:6.1f} A {cA[i]:6.1f} B {cB[i]:6.1f} us flushes {nfl[i]}")
+    print(f"    tile ({i % tx},{i // tx}) start +{rel[i] / 1e3:8.1f} us dur {dur[i] / 1e3:8.1f} us prims {prims[i]:7d} frags {frags[i]:7d}  A0 {cA0[i]:6.1f} A {cA[i]:6.1f} B {cB[i]:6.1f} pre {cPre[i]:5.1f} F3 {cF3[i]:6.1f} F12 {cF12[i]:6.1f} us flushes {nfl[i]} tested {buf[i, 11]}/{buf[i, 12]}")
 end = (rel + dur)
 print(f"  last tile ends at +{end.max() / 1e3:.1f} us; tiles starting after 50% of that: {(rel > end.max() / 2).sum()}")
 rows = dur.reshape(ty, tx).sum(axis=1) / 1e3

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- the headline benchmark of the draw path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c3|c2|c0|c0_4k]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c3|c2|c0|c0_4k|c5]
 
 Workload (config.workload): BASELINE.json configs[2], the configuration the metric is quoted on --
 a synthetic 10M tiny-triangle mesh at 3840x2160 (heavy near-plane clipping, ~45 % clockwise
@@ -74,6 +74,8 @@ def make_scene(name: str):
         return S.config_c0(), 4, "Benchmark.cpp: 40 960 random triangles, 640x480, Span, flat shader"
     if name == "c0_4k":
         return S.config_c0(3840, 2160), 4, "Benchmark.cpp's triangles at 3840x2160, Span, flat shader"
+    if name == "c5":
+        return S.config_c5(), 4, "BASELINE.json configs[4]: 50M perspective-textured triangles (5 layers), 7680x4320, Block, CullMode::CW"
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -194,7 +196,7 @@ def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
     from softwarerenderer_b200 import api
-    from softwarerenderer_b200.dist import TileComposite
+    from softwarerenderer_b200.dist import TileComposite, TileMirror
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -291,16 +293,32 @@ def run_gpu_arm(args):
     r.finish()
     tile = r.stats().last_tile_size
     if world > 1:
-        comp = TileComposite(r, W, H, tile, rank, world, dev)
+        if args.composite == "mirror":
+            # fused composite: the tile kernel stores finished tiles into the peers' surfaces (CUDA IPC / NVLink);
+            # per step only a one-word NCCL all-reduce remains, as the barrier
+            comp = TileMirror(r, api.RT_COLOR, targets[api.RT_COLOR].data_ptr(), rank, world, dev)
+            clear()
+            comp.barrier()
+        else:
+            comp = TileComposite(r, W, H, tile, rank, world, dev)
 
     # ---- fragments per draw (deterministic): summed over ranks
     clear()
+    if isinstance(comp, TileMirror):
+        comp.barrier()                    # no peer stores into a surface that is still being cleared
     r.resetStats()
     step_resident()
     r.finish()
     frag_t = torch.tensor([int(r.stats().fragments)], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(frag_t)
+        # after the composite every rank must hold the same, complete frame
+        sums = torch.stack([targets[api.RT_COLOR].to(torch.int64).sum(), (targets[api.RT_COLOR] != 0).sum()])
+        lo, hi = sums.clone(), sums.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        if not torch.equal(lo, hi):
+            raise SystemExit(f"composite differs between ranks: {lo.tolist()} vs {hi.tolist()}")
     fragments = int(frag_t.item())
 
     for _ in range(args.warmup):
@@ -353,7 +371,7 @@ def run_gpu_arm(args):
             "dtype": "f32", "data": "synthetic",
             "triangles_per_s": scene.num_primitives / (ms_step * 1e-3),
             "fragments_per_step": fragments, "triangles_per_step": scene.num_primitives,
-            "config": {"workload": wl, "tile_size": tile, "parallelism": f"sort-first tiles x{world}" if world > 1 else "single GPU",
+            "config": {"workload": wl, "tile_size": tile, "parallelism": (f"sort-first tiles x{world}, composite: " + ("tile kernel stores to peer surfaces over NVLink + 1-word NCCL barrier" if args.composite == "mirror" else "pack + NCCL all-gather + unpack")) if world > 1 else "single GPU",
                        "l2": "inputs larger than L2: 240 MB of indices + vertices are re-read every step (126 MB L2)"
                              if scene.indices.nbytes + scene.vertices.nbytes > 126e6 else "inputs fit in L2 (no flush between steps)",
                        "clear": "render targets cleared once before timing (the Gouraud shader overwrites)"},
@@ -385,6 +403,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3")
+    ap.add_argument("--composite", default="mirror", choices=["mirror", "nccl"],
+                    help="N>1: fused peer stores from the tile kernel (default) or pack + NCCL all-gather + unpack")
     ap.add_argument("--tile", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     args = ap.parse_args()

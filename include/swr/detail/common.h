@@ -141,6 +141,8 @@ struct TileArgs {
     int32_t scMinX, scMinY, scMaxX, scMaxY;
     unsigned long long *fragCounter;
     const uint32_t *errorFlag;
+    int32_t mirrorSlot, mirrorCount; // finished tiles of render target `mirrorSlot` are also stored to mirror[0..mirrorCount)
+    void *mirror[SWR_MAX_TILE_MIRRORS];   // surfaces of the same pitch / size, typically the peers' framebuffers (NVLink stores)
     uint32_t *tileStats;             // optional debug: 16 words per tile {globaltimer ns start, ns duration, primitives, fragments, A0/A/B clocks >> 4 of thread 0, flushes, flush prologue / F3 / F1+F2 clocks >> 4, records tested, groups tested, 0...}
 };
 

@@ -501,37 +501,47 @@ SWR_HD void shadePointFragment(const TileArgs &t, uint32_t rec, int px, int py, 
 // Shared-memory layout is block-linear: pixel (lx, ly) of the tile lives at word
 // ((ly/8)*BPR + lx/8)*64 + (ly%8)*8 + lx%8, so one 8x8 block is 256 contiguous bytes and a full
 // block round of 32 lanes touches 32 distinct banks.
+template <int TLOG, bool STORE>
+SWR_D void moveSlot(const TileArgs &t, char *g, int pitch, uint32_t *sm, int X0, int Y0)
+{
+    constexpr int T = 1 << TLOG, BPR = T / 8;
+    const bool vec = ((((uintptr_t)g) | (uintptr_t)pitch) & 15) == 0 && (t.rtWidth & 3) == 0;
+    if (vec) {
+        for (int i = threadIdx.x; i < T * T / 4; i += kTileThreads) {
+            const int ly = i / (T / 4), lx = (i % (T / 4)) * 4;
+            const int x = X0 + lx, y = Y0 + ly;
+            if (x < t.rtWidth && y < t.rtHeight) {
+                uint4 *gp = (uint4 *)(g + (size_t)y * pitch + (size_t)x * 4);
+                uint4 *sp = (uint4 *)(sm + (((ly >> 3) * BPR + (lx >> 3)) * 64 + (ly & 7) * 8 + (lx & 7)));
+                if (STORE) *gp = *sp; else *sp = *gp;
+            }
+        }
+    } else {
+        for (int i = threadIdx.x; i < T * T; i += kTileThreads) {
+            const int ly = i / T, lx = i % T;
+            const int x = X0 + lx, y = Y0 + ly;
+            if (x < t.rtWidth && y < t.rtHeight) {
+                uint32_t *gp = (uint32_t *)(g + (size_t)y * pitch + (size_t)x * 4);
+                uint32_t *sp = sm + (((ly >> 3) * BPR + (lx >> 3)) * 64 + (ly & 7) * 8 + (lx & 7));
+                if (STORE) *gp = *sp; else *sp = *gp;
+            }
+        }
+    }
+}
+
 template <int TLOG, int NRT, bool STORE>
 SWR_D void moveTile(const TileArgs &t, char *rtSmem, int X0, int Y0)
 {
-    constexpr int T = 1 << TLOG, BPR = T / 8;
+    constexpr int T = 1 << TLOG;
 #pragma unroll 1
-    for (int s = 0; s < NRT; ++s) {
-        char *g = (char *)t.rt[s].ptr;
-        const int pitch = t.rt[s].pitch;
-        uint32_t *sm = (uint32_t *)(rtSmem + (size_t)s * T * T * 4);
-        const bool vec = ((((uintptr_t)g) | (uintptr_t)pitch) & 15) == 0 && (t.rtWidth & 3) == 0;
-        if (vec) {
-            for (int i = threadIdx.x; i < T * T / 4; i += kTileThreads) {
-                const int ly = i / (T / 4), lx = (i % (T / 4)) * 4;
-                const int x = X0 + lx, y = Y0 + ly;
-                if (x < t.rtWidth && y < t.rtHeight) {
-                    uint4 *gp = (uint4 *)(g + (size_t)y * pitch + (size_t)x * 4);
-                    uint4 *sp = (uint4 *)(sm + (((ly >> 3) * BPR + (lx >> 3)) * 64 + (ly & 7) * 8 + (lx & 7)));
-                    if (STORE) *gp = *sp; else *sp = *gp;
-                }
-            }
-        } else {
-            for (int i = threadIdx.x; i < T * T; i += kTileThreads) {
-                const int ly = i / T, lx = i % T;
-                const int x = X0 + lx, y = Y0 + ly;
-                if (x < t.rtWidth && y < t.rtHeight) {
-                    uint32_t *gp = (uint32_t *)(g + (size_t)y * pitch + (size_t)x * 4);
-                    uint32_t *sp = sm + (((ly >> 3) * BPR + (lx >> 3)) * 64 + (ly & 7) * 8 + (lx & 7));
-                    if (STORE) *gp = *sp; else *sp = *gp;
-                }
-            }
-        }
+    for (int s = 0; s < NRT; ++s)
+        moveSlot<TLOG, STORE>(t, (char *)t.rt[s].ptr, t.rt[s].pitch, (uint32_t *)(rtSmem + (size_t)s * T * T * 4), X0, Y0);
+    // Sort-first composite fused into the store: the finished tile of one slot also goes to the peers'
+    // surfaces (plain stores through NVLink peer mappings; they overlap the tiles still being shaded).
+    if (STORE && t.mirrorCount > 0 && t.mirrorSlot < NRT) {
+#pragma unroll 1
+        for (int m = 0; m < t.mirrorCount; ++m)
+            moveSlot<TLOG, true>(t, (char *)t.mirror[m], t.rt[t.mirrorSlot].pitch, (uint32_t *)(rtSmem + (size_t)t.mirrorSlot * T * T * 4), X0, Y0);
     }
 }
 

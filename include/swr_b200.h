@@ -44,6 +44,7 @@ enum { SWR_RASTER_SPAN = 0, SWR_RASTER_BLOCK = 1, SWR_RASTER_ADAPTIVE = 2 };    
 #define SWR_BATCH_PRIMS 1024        /* VertexProcessor.cpp:110 */
 #define SWR_MAX_POLY 12             /* clipped polygon cap (9 in general position; see oracle/swr_scene.h) */
 #define SWR_ORDINAL_STRIDE 10240u   /* emission ordinal = batch * stride + slot */
+#define SWR_MAX_TILE_MIRRORS 7
 #define SWR_MAX_RENDER_TARGETS 12
 #define SWR_MAX_UNIFORM_BYTES 1024
 
@@ -183,6 +184,20 @@ SWR_API int swr_flush_l2(swr_context *ctx);   /* overwrites a 256 MiB scratch bu
 SWR_API int swr_pack_tiles(swr_context *ctx, int slot, int rank, int world, int tile_size, void *dst_device);
 SWR_API int swr_unpack_tiles(swr_context *ctx, int slot, int rank, int world, int tile_size, const void *src_device);
 SWR_API int64_t swr_owned_tile_count(int width, int height, int tile_size, int rank, int world);
+
+/* Composite fused into the tile kernel: every finished tile of render-target slot `slot` is also stored to
+ * `count` (<= SWR_MAX_TILE_MIRRORS) other surfaces of the same pitch and size -- the peers' framebuffers, mapped
+ * with swr_ipc_open, so the stores travel over NVLink while the remaining tiles are still being shaded and no
+ * pack / all-gather / unpack pass is needed.  Tiles that no primitive touched are not stored (every rank is
+ * expected to clear its surface the same way); the host provides the cross-rank barriers: one after the draws
+ * (before a mirror is read) and one between clearing a mirrored surface and the first draw of the next frame.
+ * count = 0 switches it off. */
+SWR_API int swr_set_tile_mirrors(swr_context *ctx, int slot, int count, void *const *surfaces);
+/* CUDA IPC plumbing for the above: handle (64 bytes) + offset of a device pointer inside its allocation,
+ * and the mapping of such a handle into this process / device. */
+SWR_API int swr_ipc_get_handle(const void *device_ptr, void *handle64, int64_t *offset);
+SWR_API int swr_ipc_open(swr_context *ctx, const void *handle64, int64_t offset, void **device_ptr);
+SWR_API int swr_ipc_close(swr_context *ctx, void *device_ptr);
 
 /* ---- debugging ------------------------------------------------------------------------------ */
 /* Copies the geometry stage's records of the last pass to host arrays (any may be NULL):

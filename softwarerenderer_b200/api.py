@@ -125,6 +125,19 @@ class Rasterizer:
     def setTilePartition(self, rank: int, world: int):
         _lib.check(lib.swr_set_tile_partition(self._ctx, rank, world), "setTilePartition")
 
+    def setTileMirrors(self, slot: int, surfaces):
+        """Finished tiles of render target `slot` are also stored to these device surfaces (peers' framebuffers)."""
+        arr = (C.c_void_p * max(len(surfaces), 1))(*[C.c_void_p(int(p)) for p in surfaces])
+        _lib.check(lib.swr_set_tile_mirrors(self._ctx, slot, len(surfaces), arr), "setTileMirrors")
+
+    def ipcOpen(self, handle: bytes, offset: int) -> int:
+        out = C.c_void_p()
+        _lib.check(lib.swr_ipc_open(self._ctx, handle, offset, C.byref(out)), "ipcOpen")
+        return int(out.value)
+
+    def ipcClose(self, ptr: int):
+        _lib.check(lib.swr_ipc_close(self._ctx, C.c_void_p(ptr)), "ipcClose")
+
     def setScratchLimit(self, nbytes: int):
         _lib.check(lib.swr_set_scratch_limit(self._ctx, nbytes), "setScratchLimit")
 
@@ -178,6 +191,14 @@ class Rasterizer:
 
     def fill32(self, dst: int, value: int, count: int):
         _lib.check(lib.swr_memset32(self._ctx, dst, value & 0xFFFFFFFF, count), "memset32")
+
+
+def ipc_handle(device_ptr: int):
+    """(64-byte CUDA IPC handle, offset) of a device pointer, to be opened by a peer process with Rasterizer.ipcOpen."""
+    h = C.create_string_buffer(64)
+    off = C.c_int64()
+    _lib.check(lib.swr_ipc_get_handle(C.c_void_p(int(device_ptr)), h, C.byref(off)), "ipc_handle")
+    return h.raw, int(off.value)
 
 
 class VertexProcessor:

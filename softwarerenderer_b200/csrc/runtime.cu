@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include <swr_b200.h>
@@ -141,6 +142,9 @@ struct swr_context {
     // scratch
     DevBuf dbgVerts, stageIdx, l2flush, ownedIdx, tileStats;
     bool debugTileStats = false;
+    int mirrorSlot = 0, mirrorCount = 0;
+    void *mirror[SWR_MAX_TILE_MIRRORS] = {};
+    std::vector<std::pair<void *, void *>> ipcOpened;   // {pointer handed out, mapped base}
     int lastTiles = 0;
     int ownedKey[5] = { 0, 0, 0, 0, 0 };   // {tile size, rank, world, width, height} of ownedIdx
     DevBuf stageAttrib[SWR_MAX_VERTEX_ATTRIBS];
@@ -258,9 +262,9 @@ __global__ void fill32Kernel(uint32_t *dst, uint32_t value, size_t count)
     for (; i < count; i += stride) dst[i] = value;
 }
 
-int chooseTileShift(const swr_context *c, int renderTargets)
+int chooseTileShift(const swr_context *c, int renderTargets, size_t primitives)
 {
-    auto fits64 = [&]() { return (size_t)renderTargets * 64 * 64 * 4 + 80 * 1024 <= (size_t)227 * 1024; };
+    auto fits64 = [&]() { return (size_t)renderTargets * 64 * 64 * 4 + 96 * 1024 <= (size_t)227 * 1024; };
     int req = c->tileSizeReq;
     if (req == 0) {
         const char *env = getenv("SWR_TILE_SIZE");
@@ -268,10 +272,14 @@ int chooseTileShift(const swr_context *c, int renderTargets)
     }
     if (req == 64 && fits64()) return 6;
     if (req == 32) return 5;
-    // 64-pixel tiles amortise the binning scans better, 32-pixel tiles balance better: take 64 only
-    // when this rank still gets >= 1024 of them
+    // 64-pixel tiles amortise the binning scans better, 32-pixel tiles balance better and give the shading
+    // phase four times as many CTAs: take 64 only for meshes of pixel-sized triangles (fewer than 1.5 surface
+    // pixels per primitive) and when this rank still gets >= 1024 tiles.  Measured on B200 (ms, 32 / 64):
+    // 10M tiny triangles at 4K 1.28 / 1.09, 1M-triangle grid at 1080p 0.31 / 0.34, Benchmark.cpp's 40960 large
+    // triangles at 4K 12.9 / 22.6.
     const long tiles64 = (long)((c->rtW + 63) / 64) * ((c->rtH + 63) / 64);
-    return (tiles64 / (c->world > 0 ? c->world : 1) >= 1024 && fits64()) ? 6 : 5;
+    const bool tiny = (double)primitives * 1.5 >= (double)c->rtW * (double)c->rtH;
+    return (tiny && tiles64 / (c->world > 0 ? c->world : 1) >= 1024 && fits64()) ? 6 : 5;
 }
 
 // One draw = one or more passes of {geometry kernel, tile kernel}.
@@ -360,7 +368,7 @@ int drawCommon(swr_context *c, int drawMode, size_t count, const int32_t *indice
     }
 
     // ---- pass plan
-    const int tileShift = chooseTileShift(c, ps->render_targets);
+    const int tileShift = chooseTileShift(c, ps->render_targets, count / (size_t)(drawMode == SWR_DRAW_TRIANGLE ? 3 : drawMode == SWR_DRAW_LINE ? 2 : 1));
     const int T = 1 << tileShift;
     const int tilesX = (c->rtW + T - 1) / T, tilesY = (c->rtH + T - 1) / T;
     const int nA = ps->avar_count, nP = ps->pvar_count, useZ = ps->interpolate_z, useW = ps->interpolate_w;
@@ -432,6 +440,9 @@ int drawCommon(swr_context *c, int drawMode, size_t count, const int32_t *indice
     t.chunkWords = chunkWords;
     t.tilesX = tilesX; t.tilesY = tilesY;
     t.rank = c->rank; t.world = c->world;
+    t.mirrorSlot = c->mirrorSlot;
+    t.mirrorCount = c->mirrorCount;
+    for (int m = 0; m < SWR_MAX_TILE_MIRRORS; ++m) t.mirror[m] = m < c->mirrorCount ? c->mirror[m] : nullptr;
     t.rtWidth = c->rtW; t.rtHeight = c->rtH;
     t.numRT = ps->render_targets;
     for (int s = 0; s < SWR_MAX_RENDER_TARGETS; ++s) t.rt[s] = c->rt[s];
@@ -562,6 +573,7 @@ void swr_destroy(swr_context *c)
     for (DevBuf *b : bufs) b->release();
     for (ScratchSet &ss : c->sets) ss.release();
     for (int i = 0; i < SWR_MAX_VERTEX_ATTRIBS; ++i) c->stageAttrib[i].release();
+    for (auto &o : c->ipcOpened) cudaIpcCloseMemHandle(o.second);
     if (c->hostFlags) cudaFreeHost(c->hostFlags);
     cudaEvent_t evs[] = { c->evGeom0, c->evGeom1, c->evTile0, c->evTile1, c->evTimer0, c->evTimer1, c->evDrawStart,
                           c->sets[0].geomDone, c->sets[0].tileDone, c->sets[1].geomDone, c->sets[1].tileDone };
@@ -937,6 +949,78 @@ int swr_pack_tiles(swr_context *c, int slot, int rank, int world, int tile_size,
 int swr_unpack_tiles(swr_context *c, int slot, int rank, int world, int tile_size, const void *src_device)
 {
     return exchangeTiles(c, slot, rank, world, tile_size, const_cast<void *>(src_device), false);
+}
+
+int swr_set_tile_mirrors(swr_context *c, int slot, int count, void *const *surfaces)
+{
+    if (!c) return fail(-1, "null context");
+    if (count < 0 || count > SWR_MAX_TILE_MIRRORS) return fail(-2, "at most %d mirrors", SWR_MAX_TILE_MIRRORS);
+    if (count > 0 && (slot < 0 || slot >= SWR_MAX_RENDER_TARGETS || !surfaces)) return fail(-2, "bad mirror slot / surfaces");
+    for (int m = 0; m < count; ++m)
+        if (!surfaces[m]) return fail(-2, "mirror surface %d is null", m);
+    c->mirrorSlot = slot;
+    c->mirrorCount = count;
+    for (int m = 0; m < count; ++m) c->mirror[m] = surfaces[m];
+    return 0;
+}
+
+// The allocation that holds `p`: cuMemGetAddressRange through the runtime's driver entry point (no libcuda link).
+static int allocationBase(const void *p, void **base)
+{
+    typedef int (*GetRange)(unsigned long long *, size_t *, unsigned long long);
+    static GetRange fn = nullptr;
+    if (!fn) {
+        void *sym = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &sym, cudaEnableDefault, &q) != cudaSuccess || !sym)
+            return fail(-100, "cuMemGetAddressRange is not available");
+        fn = (GetRange)sym;
+    }
+    unsigned long long b = 0;
+    size_t sz = 0;
+    if (fn(&b, &sz, (unsigned long long)(uintptr_t)p) != 0) return fail(-2, "not a device allocation");
+    *base = (void *)(uintptr_t)b;
+    return 0;
+}
+
+int swr_ipc_get_handle(const void *device_ptr, void *handle64, int64_t *offset)
+{
+    if (!device_ptr || !handle64 || !offset) return fail(-1, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size is part of the ABI");
+    void *base = nullptr;
+    if (int rc = allocationBase(device_ptr, &base)) return rc;
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(cudaIpcGetMemHandle(&h, base));
+    memcpy(handle64, &h, 64);
+    *offset = (int64_t)((const char *)device_ptr - (const char *)base);
+    return 0;
+}
+
+int swr_ipc_open(swr_context *c, const void *handle64, int64_t offset, void **device_ptr)
+{
+    if (!c || !handle64 || !device_ptr) return fail(-1, "null argument");
+    if (int rc = setDevice(c)) return rc;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void *base = nullptr;
+    CUDA_TRY(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+    *device_ptr = (char *)base + offset;
+    c->ipcOpened.push_back({ *device_ptr, base });
+    return 0;
+}
+
+int swr_ipc_close(swr_context *c, void *device_ptr)
+{
+    if (!c) return fail(-1, "null context");
+    if (int rc = setDevice(c)) return rc;
+    for (size_t i = 0; i < c->ipcOpened.size(); ++i)
+        if (c->ipcOpened[i].first == device_ptr) {
+            CUDA_TRY(cudaStreamSynchronize(c->stream));
+            CUDA_TRY(cudaIpcCloseMemHandle(c->ipcOpened[i].second));
+            c->ipcOpened.erase(c->ipcOpened.begin() + (long)i);
+            return 0;
+        }
+    return fail(-2, "pointer was not opened with swr_ipc_open");
 }
 
 int swr_debug_enable_tile_stats(swr_context *c, int enable)

@@ -92,3 +92,39 @@ class TileComposite:
             if peer != r:
                 _lib.check(lib.swr_unpack_tiles(self.r.ctx, slot, peer, w, self.tile, self.recv.data_ptr() + peer * n * 4),
                            "unpack_tiles")
+
+
+class TileMirror:
+    """Composite fused into the tile kernel: every rank maps the peers' surface of one render-target slot
+    (CUDA IPC over NVLink) and its tile kernel stores each finished tile to all of them, so after the draws
+    plus one barrier every rank holds the whole frame -- no pack / all-gather / unpack pass.  torch.distributed
+    only carries the 64-byte handles at set-up and the barrier.
+
+    Contract (see swr_set_tile_mirrors): all ranks clear the surface the same way, and call barrier() between
+    that clear and the first draw of a frame as well as after the last draw, before the surface is read."""
+
+    def __init__(self, rasterizer, slot: int, surface_ptr: int, rank: int, world: int, device):
+        import torch
+        import torch.distributed as dist
+        from . import api
+        self.r, self.slot, self.rank, self.world = rasterizer, slot, rank, world
+        mine = api.ipc_handle(surface_ptr)
+        handles = [None] * world
+        dist.all_gather_object(handles, mine)
+        self.peers = [rasterizer.ipcOpen(h, off) for i, (h, off) in enumerate(handles) if i != rank]
+        rasterizer.setTileMirrors(slot, self.peers)
+        self._token = torch.zeros(1, dtype=torch.int32, device=device)
+
+    def barrier(self) -> None:
+        """Stream-ordered cross-rank barrier (a one-word NCCL all-reduce on torch's current stream)."""
+        import torch.distributed as dist
+        dist.all_reduce(self._token)
+
+    def run(self, slot: int) -> None:       # same call shape as TileComposite.run
+        self.barrier()
+
+    def close(self) -> None:
+        self.r.setTileMirrors(self.slot, [])
+        for p in self.peers:
+            self.r.ipcClose(p)
+        self.peers = []

@@ -155,6 +155,54 @@ def test_tile_partition_union_equals_full(oracle, renderers):
     assert not common.diff_buffers(acc, want, ("count", "prim_id"))
 
 
+def test_tile_mirrors_compose_the_frame_on_every_rank(oracle):
+    """swr_set_tile_mirrors: four ranks (here four contexts on one GPU) each render their own tiles and store
+    every finished tile into the other three surfaces as well; afterwards EVERY surface holds the full frame.
+    On a multi-GPU box the same stores go to IPC-mapped peer memory (tools/mirror_check.py)."""
+    from softwarerenderer_b200 import api
+    from softwarerenderer_b200.api import SceneRenderer
+    scene = S.config_c2(nx=120, ny=80, width=480, height=270)
+    want = oracle.run(scene, "oracle")
+    world = 4
+    srs = [SceneRenderer(scene.width, scene.height) for _ in range(world)]
+    for rank, sr in enumerate(srs):
+        sr.r.setTilePartition(rank, world)
+        sr.targets.clear()
+        sr.r.setTileMirrors(api.RT_COLOR, [o.targets.ptr(api.RT_COLOR) for i, o in enumerate(srs) if i != rank])
+    for sr in srs:
+        sr.r.finish()
+    frags = 0
+    for sr in srs:
+        sr.draw(scene)
+        frags += sr.r.stats().fragments
+    assert frags == want["fragments"]
+    for rank, sr in enumerate(srs):
+        out = np.empty((scene.height, scene.width), dtype=np.uint32)
+        sr.r.download(sr.targets.ptr(api.RT_COLOR), out)
+        sr.r.finish()
+        assert np.array_equal(out, want["color"].reshape(out.shape)), f"surface of rank {rank} is not the full frame"
+        handle, off = api.ipc_handle(sr.targets.ptr(api.RT_COLOR))
+        assert len(handle) == 64 and off >= 0
+    for sr in srs:
+        sr.r.setTileMirrors(api.RT_COLOR, [])
+        sr.close()
+
+
+def test_tile_mirrors_across_gpus():
+    """The same through CUDA IPC on two GPUs (skipped on a one-GPU box)."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(root, "tools", "mirror_check.py")]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    assert p.returncode == 0 and "MIRROR OK" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
+
+
 def test_gpu_pack_unpack_matches_host_layout(renderers):
     """swr_pack_tiles / swr_unpack_tiles produce exactly the layout of softwarerenderer_b200.dist."""
     from softwarerenderer_b200 import _lib, dist as D

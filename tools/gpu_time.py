@@ -22,6 +22,8 @@ SCENES = {
     "c3s": lambda: S.config_c3(raster_mode=S.RASTER_SPAN),
     "c4l": S.config_c4,
     "c4p": lambda: S.config_c4(draw_mode=S.DRAW_POINT),
+    "c5": S.config_c5,
+    "c5a": lambda: S.config_c5(ps=S.PS_TEXTURED_ANISO),
 }
 
 

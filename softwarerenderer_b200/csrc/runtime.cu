@@ -110,6 +110,8 @@ struct swr_context {
     cudaStream_t stream = nullptr;      // main stream: tile kernels, everything the caller orders against
     cudaStream_t ownStream = nullptr;   // created by swr_create
     cudaStream_t aux = nullptr;         // geometry kernels and their input staging
+    cudaStream_t copy = nullptr;        // host -> device staging of big draws, pass by pass (created on first use)
+    std::vector<cudaEvent_t> idxReady;  // one per pass of the current draw
     cudaEvent_t evGeom0 = nullptr, evGeom1 = nullptr, evTile0 = nullptr, evTile1 = nullptr, evTimer0 = nullptr, evTimer1 = nullptr,
                 evDrawStart = nullptr;
     ScratchSet sets[2];
@@ -322,9 +324,22 @@ int drawCommon(swr_context *c, int drawMode, size_t count, const int32_t *indice
     GeomArgs g;
     memset(&g, 0, sizeof(g));
     const int32_t *devIndices = indices;
+    // Host indices of a big draw are streamed: the staging copies run on their own stream, attributes
+    // first, then the indices pass by pass, and pass k's kernels only wait for their own slice -- the
+    // PCIe transfer of pass k+1 runs under the kernels of pass k.
+    const size_t idxBytes = nprims * per * sizeof(int32_t);
+    const bool streamIdx = !c->pipeline && !rasterVerts && !isDevicePointer(indices) && idxBytes >= ((size_t)32 << 20) &&
+                           !getenv("SWR_NO_INDEX_STREAMING");
+    cudaStream_t hs = gs;                                    // stream of the staging copies
+    if (streamIdx) {
+        if (!c->copy) CUDA_TRY(cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking));
+        hs = c->copy;
+        CUDA_TRY(cudaEventRecord(c->evDrawStart, c->stream));             // the staging buffers may still be read by earlier draws
+        CUDA_TRY(cudaStreamWaitEvent(hs, c->evDrawStart, 0));
+    }
     if (!isDevicePointer(indices)) {
         if (int rc = c->stageIdx.reserve(count * sizeof(int32_t))) return rc;
-        CUDA_TRY(cudaMemcpyAsync(c->stageIdx.ptr, indices, nprims * per * sizeof(int32_t), cudaMemcpyHostToDevice, gs));
+        if (!streamIdx) CUDA_TRY(cudaMemcpyAsync(c->stageIdx.ptr, indices, idxBytes, cudaMemcpyHostToDevice, gs));
         devIndices = static_cast<const int32_t *>(c->stageIdx.ptr);
     }
     if (rasterVerts) {
@@ -343,7 +358,7 @@ int drawCommon(swr_context *c, int drawMode, size_t count, const int32_t *indice
             if (!isDevicePointer(a.ptr)) {
                 if (a.bytes == 0) return fail(-9, "vertex attribute %d is host memory: its extent is required (bytes > 0)", i);
                 if (int rc = c->stageAttrib[i].reserve(a.bytes)) return rc;
-                CUDA_TRY(cudaMemcpyAsync(c->stageAttrib[i].ptr, a.ptr, a.bytes, cudaMemcpyHostToDevice, gs));
+                CUDA_TRY(cudaMemcpyAsync(c->stageAttrib[i].ptr, a.ptr, a.bytes, cudaMemcpyHostToDevice, hs));
                 dp = c->stageAttrib[i].ptr;
             }
             g.attribPtr[i] = dp;
@@ -388,6 +403,14 @@ int drawCommon(swr_context *c, int drawMode, size_t count, const int32_t *indice
             want = env ? atoi(env) : 1;   // measured: one pass per draw is fastest (every tile pass has its own tail)
         }
         want = std::max(1, std::min(want, 64));
+        const size_t per_pass = ((nprims + want - 1) / want + kBatch - 1) / kBatch * kBatch;
+        passPrims = std::min(passPrims, std::max<size_t>(kBatch, per_pass));
+    }
+    if (streamIdx) {
+        // 2..8 passes of >= 32 MB of indices each: enough slices to hide the kernels, few enough tile passes
+        const char *env = getenv("SWR_STREAM_SLICE_MB");
+        const size_t slice = (size_t)std::max(1, env ? atoi(env) : 32) << 20;
+        const size_t want = std::max<size_t>(2, std::min<size_t>(8, idxBytes / slice));
         const size_t per_pass = ((nprims + want - 1) / want + kBatch - 1) / kBatch * kBatch;
         passPrims = std::min(passPrims, std::max<size_t>(kBatch, per_pass));
     }
@@ -458,10 +481,27 @@ int drawCommon(swr_context *c, int drawMode, size_t count, const int32_t *indice
     swr_launch_fn tileLaunch = ps->launch_tiles[drawMode][tileShift - 5];
     const uint32_t extrasBegin = (uint32_t)firstsCap;
 
+    if (streamIdx) {
+        const size_t npass = (nprims + passPrims - 1) / passPrims;
+        while (c->idxReady.size() < npass) {
+            cudaEvent_t ev;
+            CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            c->idxReady.push_back(ev);
+        }
+        size_t k = 0;
+        for (size_t first = 0; first < nprims; first += passPrims, ++k) {
+            const size_t n = std::min(passPrims, nprims - first);
+            CUDA_TRY(cudaMemcpyAsync(static_cast<int32_t *>(c->stageIdx.ptr) + first * per, indices + first * per, n * per * sizeof(int32_t),
+                                     cudaMemcpyHostToDevice, hs));
+            CUDA_TRY(cudaEventRecord(c->idxReady[k], hs));
+        }
+    }
     CUDA_TRY(cudaEventRecord(c->evGeom0, gs));
     bool firstPass = true;
-    for (size_t first = 0; first < nprims; first += passPrims) {
+    size_t passIndex = 0;
+    for (size_t first = 0; first < nprims; first += passPrims, ++passIndex) {
         const size_t n = std::min(passPrims, nprims - first);
+        if (streamIdx) CUDA_TRY(cudaStreamWaitEvent(gs, c->idxReady[passIndex], 0));
         ScratchSet &ss = c->sets[c->pipeline ? (c->passSeq & 1) : 0];
         Counters *dc = static_cast<Counters *>(ss.counters.ptr);
         g.indices = devIndices + first * per;
@@ -579,6 +619,8 @@ void swr_destroy(swr_context *c)
                           c->sets[0].geomDone, c->sets[0].tileDone, c->sets[1].geomDone, c->sets[1].tileDone };
     for (cudaEvent_t ev : evs)
         if (ev) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : c->idxReady) cudaEventDestroy(ev);
+    if (c->copy) { cudaStreamSynchronize(c->copy); cudaStreamDestroy(c->copy); }
     if (c->aux) cudaStreamDestroy(c->aux);
     if (c->ownStream) cudaStreamDestroy(c->ownStream);
     delete c;

@@ -112,6 +112,21 @@ def test_multi_pass_equals_single_pass(oracle, renderers):
     sr.close()
 
 
+def test_streamed_host_indices(oracle):
+    """Host index arrays of 32 MB and more are uploaded pass by pass under the kernels of the previous pass;
+    twice in a row (the staging buffers are reused), results unchanged."""
+    from softwarerenderer_b200.api import SceneRenderer
+    scene = S.config_c3(1300, 1100, 960, 540, ps=S.PS_COUNT_ID)
+    assert scene.indices.nbytes >= 32 << 20
+    want = oracle.run(scene, "oracle")
+    sr = SceneRenderer(scene.width, scene.height)
+    for _ in range(2):
+        got = sr.render(scene)
+        assert got["stats"].passes >= 2
+        check(got, want, "streamed")
+    sr.close()
+
+
 def test_device_resident_inputs(oracle, renderers):
     """Vertex / index buffers already in HBM are used in place."""
     scene = S.config_c2(100, 50, 480, 270)

@@ -515,8 +515,11 @@ SWR_D void publishGroup(const GeomArgs &g, Box16 box, uint32_t group, uint32_t c
     }
 }
 
+#ifndef SWR_GEOM_MINB
+#define SWR_GEOM_MINB 1
+#endif
 template <class VS>
-__global__ void __launch_bounds__(kGeomThreads) geometryKernel(const GeomArgs g)
+__global__ void __launch_bounds__(kGeomThreads, SWR_GEOM_MINB) geometryKernel(const GeomArgs g)
 {
     constexpr int NA = VS::AVarCount, NP = VS::PVarCount;
     typedef CVert<NA, NP> V;

@@ -383,9 +383,6 @@ int drawCommon(swr_context *c, int drawMode, size_t count, const int32_t *indice
     }
 
     // ---- pass plan
-    const int tileShift = chooseTileShift(c, ps->render_targets, count / (size_t)(drawMode == SWR_DRAW_TRIANGLE ? 3 : drawMode == SWR_DRAW_LINE ? 2 : 1));
-    const int T = 1 << tileShift;
-    const int tilesX = (c->rtW + T - 1) / T, tilesY = (c->rtH + T - 1) / T;
     const int nA = ps->avar_count, nP = ps->pvar_count, useZ = ps->interpolate_z, useW = ps->interpolate_w;
     const int paramStride = paramFloats(drawMode, nA, nP, useZ, useW);
     const bool needSpan = drawMode == SWR_DRAW_TRIANGLE && c->rasterMode != SWR_RASTER_BLOCK;
@@ -414,6 +411,9 @@ int drawCommon(swr_context *c, int drawMode, size_t count, const int32_t *indice
         const size_t per_pass = ((nprims + want - 1) / want + kBatch - 1) / kBatch * kBatch;
         passPrims = std::min(passPrims, std::max<size_t>(kBatch, per_pass));
     }
+    const int tileShift = chooseTileShift(c, ps->render_targets, std::min(nprims, passPrims));   // density of ONE pass
+    const int T = 1 << tileShift;
+    const int tilesX = (c->rtW + T - 1) / T, tilesY = (c->rtH + T - 1) / T;
     const size_t firstsCap = passPrims;                                  // multiple of kBatch
     const size_t extrasCap = tri ? passPrims * (size_t)(kMaxFan - 1) : 0;
     const size_t recCap = firstsCap + extrasCap;

@@ -51,11 +51,11 @@ def load_peaks():
 
 def ncu_traffic(workload: str, tile: int, world: int):
     """dram__bytes_read.sum + dram__bytes_write.sum of the tile kernel from the committed ncu --set full capture
-    (profiles/r01_summary.json: C3, 64-pixel tiles, one GPU); None for any other configuration."""
+    (profiles/r01b_summary.json: C3, 64-pixel tiles, one GPU); None for any other configuration."""
     if workload != "c3" or tile != 64 or world != 1:
         return None
     try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "r01_summary.json")))["tile"]
+        d = json.load(open(os.path.join(ROOT, "profiles", "r01b_summary.json")))["tile"]
 
         def mb(v):
             num, unit = v.split()[:2]
@@ -196,7 +196,7 @@ def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
     from softwarerenderer_b200 import api
-    from softwarerenderer_b200.dist import TileComposite, TileMirror
+    from softwarerenderer_b200.dist import ReplicatedUpload, TileComposite, TileMirror
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -260,12 +260,20 @@ def run_gpu_arm(args):
         if comp is not None:
             comp.run(api.RT_COLOR)
 
+    repl = ReplicatedUpload([scene.vertices, scene.indices], rank, world, dev) if world > 1 else None
+
     def step_e2e():
-        v.setVertexAttribPointer(0, scene.stride, h_vert)          # host pointers: staged H2D by the library
-        v.drawElements(scene.draw_mode, count, h_idx, wait=False)
-        if comp is not None:
+        if world == 1:
+            v.setVertexAttribPointer(0, scene.stride, h_vert)      # host pointers: staged H2D by the library
+            v.drawElements(scene.draw_mode, count, h_idx, wait=False)
+        else:
+            # every rank uploads 1/N of the geometry over its own PCIe link; NCCL all-gather replicates it
+            pv, pi = repl.run()
+            v.setVertexAttribPointer(0, scene.stride, pv, nbytes=scene.vertices.nbytes)
+            v.drawElements(scene.draw_mode, count, pi, wait=False)
             comp.run(api.RT_COLOR)
-        h_color.copy_(targets[api.RT_COLOR], non_blocking=True)     # D2H of the step's result
+        if rank == 0:
+            h_color.copy_(targets[api.RT_COLOR], non_blocking=True)  # D2H of the step's result (the composed frame)
 
     def barrier():
         if world > 1:
@@ -383,7 +391,10 @@ def run_gpu_arm(args):
                          "draw": {"algorithmic_bytes": geom_b + frag_b / world, "achieved": ach_draw, "frac": ach_draw / peak,
                                   "distinct_vertices": v_ref}},
             "e2e": {"value": fragments / (ms_e2e / args.steps * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
-                    "h2d_bytes_per_step": int(scene.vertices.nbytes + scene.indices.nbytes), "d2h_bytes_per_step": int(W * H * 4)},
+                    "h2d_bytes_per_step": int(scene.vertices.nbytes + scene.indices.nbytes) if world == 1 else int(repl.h2d_bytes * world),
+                    "d2h_bytes_per_step": int(W * H * 4),
+                    "path": "host buffers -> swr_draw_elements (staged by the library, indices streamed pass by pass) -> frame to host" if world == 1 else
+                            f"each rank uploads 1/{world} of the geometry, NCCL all-gather replicates it, draw + composite, rank 0 reads the frame"},
             "gpu_launches": launches_total,
             "clocks": clocks,
         }

@@ -128,3 +128,35 @@ class TileMirror:
         for p in self.peers:
             self.r.ipcClose(p)
         self.peers = []
+
+
+class ReplicatedUpload:
+    """Host -> every GPU, for buffers that all ranks need in full (sort-first replicates the geometry): each rank
+    copies only 1/world of the bytes over its own PCIe link, then one NCCL all-gather over NVLink gives every
+    rank the whole buffer.  Several arrays are packed into one byte buffer (256-byte aligned sections)."""
+
+    def __init__(self, arrays, rank: int, world: int, device):
+        import numpy as np
+        import torch
+        self.offsets = []
+        total = 0
+        for a in arrays:
+            self.offsets.append(total)
+            total += (a.nbytes + 255) // 256 * 256
+        self.per = ((total + world - 1) // world + 255) // 256 * 256
+        self.total = total
+        host = np.zeros(self.per * world, dtype=np.uint8)
+        for a, off in zip(arrays, self.offsets):
+            host[off:off + a.nbytes] = np.ascontiguousarray(a).view(np.uint8).reshape(-1)
+        self.slice_host = torch.from_numpy(host[rank * self.per:(rank + 1) * self.per].copy()).pin_memory()
+        self.slice_dev = torch.empty(self.per, dtype=torch.uint8, device=device)
+        self.full = torch.empty(self.per * world, dtype=torch.uint8, device=device)
+        self.h2d_bytes = self.per                       # per rank and step
+
+    def run(self):
+        """Enqueue on torch's current stream; returns the device address of each array."""
+        import torch.distributed as dist
+        self.slice_dev.copy_(self.slice_host, non_blocking=True)
+        dist.all_gather_into_tensor(self.full, self.slice_dev)
+        base = self.full.data_ptr()
+        return [base + off for off in self.offsets]

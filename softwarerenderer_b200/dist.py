@@ -148,7 +148,9 @@ class ReplicatedUpload:
         host = np.zeros(self.per * world, dtype=np.uint8)
         for a, off in zip(arrays, self.offsets):
             host[off:off + a.nbytes] = np.ascontiguousarray(a).view(np.uint8).reshape(-1)
-        self.slice_host = torch.from_numpy(host[rank * self.per:(rank + 1) * self.per].copy()).pin_memory()
+        self.slice_host = torch.from_numpy(host[rank * self.per:(rank + 1) * self.per].copy())
+        if torch.cuda.is_available():
+            self.slice_host = self.slice_host.pin_memory()
         self.slice_dev = torch.empty(self.per, dtype=torch.uint8, device=device)
         self.full = torch.empty(self.per * world, dtype=torch.uint8, device=device)
         self.h2d_bytes = self.per                       # per rank and step

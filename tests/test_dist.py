@@ -63,6 +63,39 @@ def test_two_rank_composite_gloo(oracle, tile):
     assert sorted(results) == [(0, True), (1, True)]
 
 
+def _upload_worker(rank, world, port, result_q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(5)                                      # same arrays on every rank
+        verts = rng.random((1001, 7), dtype=np.float32)
+        idx = rng.integers(0, 1001, size=2999, dtype=np.int32)
+        up = D.ReplicatedUpload([verts, idx], rank, world, torch.device("cpu"))
+        up.run()
+        full = up.full.numpy()
+        ok = bool(np.array_equal(full[up.offsets[0]:up.offsets[0] + verts.nbytes].view(np.float32).reshape(verts.shape), verts) and
+                  np.array_equal(full[up.offsets[1]:up.offsets[1] + idx.nbytes].view(np.int32), idx))
+        result_q.put((rank, ok and up.h2d_bytes * world >= verts.nbytes + idx.nbytes and up.offsets[1] % 256 == 0))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_replicated_upload_gloo():
+    """Each rank contributes 1/world of the packed geometry; after the all-gather everyone holds all of it."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_upload_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(results) == [(0, True), (1, True)]
+
+
 def test_owned_tiles_partition_and_match_abi():
     from softwarerenderer_b200 import _lib
     lib = _lib.load()

@@ -141,10 +141,17 @@ struct TileArgs {
     int32_t scMinX, scMinY, scMaxX, scMaxY;
     unsigned long long *fragCounter;
     const uint32_t *errorFlag;
+    uint32_t *groupCount;            // per tile: groups listed by binKernel (bin.cuh), 0xffffffff = list overflowed; nullptr = no binning pass
+    uint32_t *groupList;             // per tile groupCap group ids, ascending
+    uint32_t groupCap;
     int32_t mirrorSlot, mirrorCount; // finished tiles of render target `mirrorSlot` are also stored to mirror[0..mirrorCount)
     void *mirror[SWR_MAX_TILE_MIRRORS];   // surfaces of the same pitch / size, typically the peers' framebuffers (NVLink stores)
     uint32_t *tileStats;             // optional debug: 16 words per tile {globaltimer ns start, ns duration, primitives, fragments, A0/A/B clocks >> 4 of thread 0, flushes, flush prologue / F3 / F1+F2 clocks >> 4, records tested, groups tested, 0...}
 };
+
+// The kernels of a user's shader TU are compiled against these argument structs, the library fills them: a TU
+// built with other headers than the library is refused when its shader is set (swr_set_*_shader).
+#define SWR_ARGS_LAYOUT ((uint32_t)(sizeof(::swr::detail::GeomArgs) * 65599u + sizeof(::swr::detail::TileArgs) * 31u + 2u))
 
 // number of floats of one params record
 SWR_HD int paramFloats(int drawMode, int nA, int nP, int useZ, int useW)

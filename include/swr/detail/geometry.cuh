@@ -692,7 +692,7 @@ void launchGeometry(const void *args, void *stream)
 template <class VS>
 const swr_vertex_shader *vertexShaderBinding(const char *name = "user")
 {
-    static const swr_vertex_shader d = { &launchGeometry<VS>, &uploadUniforms, VS::AttribCount, VS::AVarCount, VS::PVarCount, name };
+    static const swr_vertex_shader d = { &launchGeometry<VS>, &uploadUniforms, VS::AttribCount, VS::AVarCount, VS::PVarCount, name, SWR_ARGS_LAYOUT };
     return &d;
 }
 

@@ -383,7 +383,7 @@ SWR_HD void shadeTriangleFragment(const TileArgs &t, uint32_t rec, int gx, int g
         eq.e2.a = h1.z; eq.e2.b = h1.w; eq.e2.c = h2.x; eq.e2.tie = (flags & kTie2) != 0;
     }
 
-    auto chain = [&](const float a, const float b, const float c) -> float {
+    auto chain = [&](const float a, const float b, const float c) __attribute__((always_inline)) -> float {
         float v = fadd(fadd(fmul(a, xf), fmul(b, yf)), c);          // ParameterEquation::evaluate
         if (flags & kModeSpan) {
             for (int s = 0; s < ncol; ++s) v = fadd(v, a);
@@ -586,7 +586,7 @@ __global__ void __launch_bounds__(kTileThreads, SWR_TILE_MINB) tileKernel(const 
     if (timing) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tStart));
 
     // ---- flush: coverage (A) + shading (B) of the queued primitives -----------------------------
-    auto flushQueue = [&]() {
+    auto flushQueue = [&]() __attribute__((always_inline)) {
         if (nQ == 0) return;
         primsSeen += nQ;
         if (timing) { cycMark = clock64(); cycIn = cycMark; ++dbgFlush; }
@@ -623,7 +623,7 @@ __global__ void __launch_bounds__(kTileThreads, SWR_TILE_MINB) tileKernel(const 
         if (!prune && tid == 0) qItem[nQ] = nItems;       // qItem already holds the prefix F3 computed
         __syncthreads();
         if (prune) {   // re-index the surviving items: qItem = exclusive prefix of the per-primitive item counts
-            auto itemCount = [&](uint32_t q) -> uint32_t {
+            auto itemCount = [&](uint32_t q) __attribute__((always_inline)) -> uint32_t {
                 if (q >= nQ) return 0u;
                 const uint32_t rg = qRange[q];
                 const int n = ((int)((rg >> 16) & 0xff) - (int)(rg & 0xff) + 1) * ((int)(rg >> 24) - (int)((rg >> 8) & 0xff) + 1);
@@ -732,7 +732,7 @@ __global__ void __launch_bounds__(kTileThreads, SWR_TILE_MINB) tileKernel(const 
                     m = sMasks[qItem[q] + (uint32_t)k];
                 }
                 // One fragment of primitive `frec` at bit `fbit` of this block.
-                auto shadeOne = [&](uint32_t frec, int fbit) {
+                auto shadeOne = [&](uint32_t frec, int fbit) __attribute__((always_inline)) {
                     const int xx = fbit & 7, yy = fbit >> 3;
                     if (gx + xx >= t.rtWidth || gy + yy >= t.rtHeight) return;      // block sticks out of the surface
                     p.rtOffset = (b * 64 + fbit) * 4;
@@ -818,7 +818,7 @@ __global__ void __launch_bounds__(kTileThreads, SWR_TILE_MINB) tileKernel(const 
     // ---- F3: records of the listed groups -> queue ------------------------------------------------
     // Four consecutive records per thread and scan step (one 32-byte read of their boxes): a quarter of
     // the barriers, four loads in flight per thread.
-    auto drainGroups = [&]() {
+    auto drainGroups = [&]() __attribute__((always_inline)) {
         __syncthreads();                                     // gList writes of the caller are visible
         const uint32_t npairs = nGroup * 32u;
         const long long f3In = timing ? clock64() : 0;
@@ -902,6 +902,15 @@ __global__ void __launch_bounds__(kTileThreads, SWR_TILE_MINB) tileKernel(const 
     // ---- F1 + F2 ----------------------------------------------------------------------------------
     const uint32_t *row = t.tilemap + (size_t)blockIdx.x * t.chunkWords;
     const long long f12In = timing ? clock64() : 0;
+    // Normally binKernel (bin.cuh) has already listed this tile's groups; the in-kernel F1 + F2 below only
+    // run for tiles whose list overflowed its capacity, or when the binning pass is switched off.
+    const uint32_t listed = t.groupCount ? t.groupCount[blockIdx.x] : 0xffffffffu;
+    if (listed <= (uint32_t)kGroupList) {                    // (the overflow mark is 0xffffffff)
+        const uint32_t *lst = t.groupList + (size_t)blockIdx.x * t.groupCap;
+        for (uint32_t i = tid; i < listed; i += kTileThreads) gList[i] = lst[i];
+        nGroup = listed;                                     // drained by the common drainGroups() below
+        if (SWR_TILE_STATS) dbgGroups += listed;
+    } else
     for (int wb = 0; wb < t.chunkWords; wb += kTileThreads) {
         uint32_t pending = (wb + tid < t.chunkWords) ? row[wb + tid] : 0u;
         while (true) {
@@ -1031,7 +1040,7 @@ const swr_pixel_shader *pixelShaderBinding(const char *name = "user")
           { &launchTiles<PS, 2, 5>, &launchTiles<PS, 2, 6> } },
         &uploadUniforms,
         PS::AVarCount, PS::PVarCount, PS::InterpolateZ ? 1 : 0, PS::InterpolateW ? 1 : 0,
-        PS::RenderTargets, name };
+        PS::RenderTargets, name, SWR_ARGS_LAYOUT };
     return &d;
 }
 

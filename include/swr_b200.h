@@ -81,6 +81,7 @@ typedef struct swr_vertex_shader {
     swr_uniform_fn set_uniforms;     /* copies the uniform block into the shader TU's __constant__ memory */
     int32_t attrib_count, avar_count, pvar_count;
     const char *name;
+    uint32_t args_layout;            /* SWR_ARGS_LAYOUT of the headers the shader TU was compiled with */
 } swr_vertex_shader;
 
 /* What Rasterizer::setPixelShader<PS>() captures (Rasterizer.h:90-96): launchers of the tile
@@ -91,6 +92,7 @@ typedef struct swr_pixel_shader {
     int32_t avar_count, pvar_count, interpolate_z, interpolate_w;
     int32_t render_targets;             /* slots [0, render_targets) are staged in shared memory */
     const char *name;
+    uint32_t args_layout;               /* SWR_ARGS_LAYOUT of the headers the shader TU was compiled with */
 } swr_pixel_shader;
 
 SWR_API const swr_vertex_shader *swr_stock_vertex_shader(int vs_kind);

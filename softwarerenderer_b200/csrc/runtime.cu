@@ -17,6 +17,7 @@
 #include <swr_b200.h>
 #include <swr/detail/common.h>
 #include <swr/detail/geometry.cuh>
+#include <swr/detail/bin.cuh>
 
 using namespace swr::detail;
 
@@ -98,11 +99,11 @@ bool isDevicePointer(const void *p)
 // One set of per-pass scratch.  Two sets alternate so that the geometry kernel of pass k+1 (on the
 // auxiliary stream) overlaps the tile kernel of pass k (on the main stream).
 struct ScratchSet {
-    DevBuf bbox, gbox, head, params, span, tilemap, extra, counters;
+    DevBuf bbox, gbox, head, params, span, tilemap, extra, counters, groupList, groupCount;
     cudaEvent_t geomDone = nullptr, tileDone = nullptr;
     bool tilePending = false, countersInit = false;
-    size_t bytes() const { return bbox.bytes + gbox.bytes + head.bytes + params.bytes + span.bytes + tilemap.bytes + extra.bytes + counters.bytes; }
-    void release() { bbox.release(); gbox.release(); head.release(); params.release(); span.release(); tilemap.release(); extra.release(); counters.release(); }
+    size_t bytes() const { return bbox.bytes + gbox.bytes + head.bytes + params.bytes + span.bytes + tilemap.bytes + extra.bytes + counters.bytes + groupList.bytes + groupCount.bytes; }
+    void release() { bbox.release(); gbox.release(); head.release(); params.release(); span.release(); tilemap.release(); extra.release(); counters.release(); groupList.release(); groupCount.release(); }
 };
 
 struct swr_context {
@@ -275,12 +276,12 @@ int chooseTileShift(const swr_context *c, int renderTargets, size_t primitives)
     if (req == 64 && fits64()) return 6;
     if (req == 32) return 5;
     // 64-pixel tiles amortise the binning scans better, 32-pixel tiles balance better and give the shading
-    // phase four times as many CTAs: take 64 only for meshes of pixel-sized triangles (fewer than 1.5 surface
-    // pixels per primitive) and when this rank still gets >= 1024 tiles.  Measured on B200 (ms, 32 / 64):
-    // 10M tiny triangles at 4K 1.28 / 1.09, 1M-triangle grid at 1080p 0.31 / 0.34, Benchmark.cpp's 40960 large
-    // triangles at 4K 12.9 / 22.6.
+    // phase four times as many CTAs: take 64 only for meshes of small triangles (fewer than 10 surface pixels per
+    // primitive of one pass) and when this rank still gets >= 1024 tiles.  Measured on B200 (ms, 32 / 64):
+    // 10M tiny triangles at 4K 1.28 / 1.13, 5 x 10M triangles at 8K 12.9 / 10.9, 1M-triangle grid at 1080p
+    // (510 tiles of 64) 0.31 / 0.35, Benchmark.cpp's 40960 large triangles at 4K 13.0 / 22.8.
     const long tiles64 = (long)((c->rtW + 63) / 64) * ((c->rtH + 63) / 64);
-    const bool tiny = (double)primitives * 1.5 >= (double)c->rtW * (double)c->rtH;
+    const bool tiny = (double)primitives * 10.0 >= (double)c->rtW * (double)c->rtH;
     return (tiny && tiles64 / (c->world > 0 ? c->world : 1) >= 1024 && fits64()) ? 6 : 5;
 }
 
@@ -421,6 +422,10 @@ int drawCommon(swr_context *c, int drawMode, size_t count, const int32_t *indice
     const size_t passBatches = passPrims / kBatch;
     const int chunkWords = (int)((2 * passBatches + 31) / 32);
 
+    // chunk + group binning as a pass of its own (bin.cuh); the per-tile list capacity is a tuning knob, tiles
+    // beyond it bin themselves inside the tile kernel
+    const bool binPass = !getenv("SWR_NO_BIN_PASS");
+    const uint32_t groupCap = tileShift == 6 ? 2048u : 1024u;          // <= kGroupList of tile.cuh
     for (ScratchSet &ss : c->sets) {
         if (int rc = ss.bbox.reserve(recCap * sizeof(Box16))) return rc;
         if (int rc = ss.gbox.reserve((recCap / kGroup + 1) * sizeof(Box16))) return rc;
@@ -429,6 +434,10 @@ int drawCommon(swr_context *c, int drawMode, size_t count, const int32_t *indice
         if (needSpan) if (int rc = ss.span.reserve(recCap * 48)) return rc;
         if (int rc = ss.tilemap.reserve((size_t)tilesX * tilesY * chunkWords * 4)) return rc;
         if (int rc = ss.extra.reserve(passBatches * sizeof(uint2))) return rc;
+        if (binPass) {
+            if (int rc = ss.groupList.reserve((size_t)tilesX * tilesY * groupCap * 4)) return rc;
+            if (int rc = ss.groupCount.reserve((size_t)tilesX * tilesY * 4)) return rc;
+        }
         if (int rc = ss.counters.reserve(sizeof(Counters))) return rc;
         if (!ss.countersInit) {
             CUDA_TRY(cudaMemset(ss.counters.ptr, 0, sizeof(Counters)));
@@ -518,6 +527,9 @@ int drawCommon(swr_context *c, int drawMode, size_t count, const int32_t *indice
         g.errorFlag = &dc->errorFlag;
         t.bbox = g.bbox; t.gbox = g.gbox; t.head = g.head; t.params = g.params; t.span = g.span;
         t.tilemap = g.tilemap;
+        t.groupList = binPass ? static_cast<uint32_t *>(ss.groupList.ptr) : nullptr;
+        t.groupCount = binPass ? static_cast<uint32_t *>(ss.groupCount.ptr) : nullptr;
+        t.groupCap = groupCap;
         t.extra = g.extra;
         t.fragCounter = &dc->fragments;
         t.errorFlag = &dc->errorFlag;
@@ -539,6 +551,10 @@ int drawCommon(swr_context *c, int drawMode, size_t count, const int32_t *indice
         }
         if (firstPass) CUDA_TRY(cudaEventRecord(c->evTile0, c->stream));
         firstPass = false;
+        if (binPass) {
+            launchBin(t, tileShift, c->stream);
+            c->stats.kernel_launches++;
+        }
         tileLaunch(&t, c->stream);
         if (gs != c->stream) {
             CUDA_TRY(cudaEventRecord(ss.tileDone, c->stream));
@@ -666,6 +682,7 @@ int swr_set_vertex_shader(swr_context *c, const swr_vertex_shader *vs)
 {
     if (!c || !vs) return fail(-1, "null argument");
     if (vs->attrib_count > SWR_MAX_VERTEX_ATTRIBS) return fail(-2, "AttribCount %d > %d", vs->attrib_count, SWR_MAX_VERTEX_ATTRIBS);  // VertexProcessor.h:80
+    if (vs->args_layout != SWR_ARGS_LAYOUT) return fail(-24, "vertex shader '%s' was compiled against other swr headers than this library: rebuild it", vs->name);
     c->vs = vs;
     return 0;
 }
@@ -690,6 +707,7 @@ int swr_set_pixel_shader(swr_context *c, const swr_pixel_shader *ps)
 {
     if (!c || !ps) return fail(-1, "null argument");
     if (ps->render_targets > SWR_MAX_RENDER_TARGETS) return fail(-2, "RenderTargets %d > %d", ps->render_targets, SWR_MAX_RENDER_TARGETS);
+    if (ps->args_layout != SWR_ARGS_LAYOUT) return fail(-24, "pixel shader '%s' was compiled against other swr headers than this library: rebuild it", ps->name);
     c->ps = ps;
     return 0;
 }

@@ -32,9 +32,6 @@
 namespace swr {
 namespace detail {
 
-#ifndef SWR_COVER_VARIANT
-#define SWR_COVER_VARIANT 1
-#endif
 #ifndef SWR_DENSE_MIN
 #define SWR_DENSE_MIN 32
 #endif
@@ -179,8 +176,7 @@ SWR_HD uint64_t coverBlock(const float4 h0, const float4 h1, const float4 h2, in
     if (all == 4) return ~0ull;                                            // drawBlock<false>
     if (all == 0 && same) return 0ull;                                     // "special case": block skipped
 
-#if SWR_COVER_VARIANT == 1
-    // variant 1: row-by-row, exact row maxima from the full 7-add chains
+    // row by row, exact row maxima from the full 7-add chains
     uint64_t mask = 0;
     float r0 = e00[0], r1 = e00[1], r2 = e00[2];
 #pragma unroll 1
@@ -206,61 +202,6 @@ SWR_HD uint64_t coverBlock(const float4 h0, const float4 h1, const float4 h2, in
     (void)a7;
     return mask;
 }
-#else
-    // Pass 1 -- which rows can hold a covered pixel.  Row yy of edge k starts at the reference's
-    // row chain value r (e00 + b + b + ...) and its maximum is r when a <= 0, else the last chain
-    // value l = ((r + a) + a) ... (7 adds).  l is first bracketed by q = r + 7a with the proven
-    // bound |l - q| <= 2^-20 * max(|r|, |q|) (+ an absolute term for the subnormal range); only
-    // when that bracket straddles zero are the 7 adds actually performed.  Exact either way.
-    uint32_t live = 0;
-    {
-        float r[3] = { e00[0], e00[1], e00[2] };
-#pragma unroll
-        for (int yy = 0; yy < 8; ++yy) {
-            bool dead = false;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                if (ea[k] <= 0) {
-                    dead = dead || !(r[k] > thr[k]);
-                } else if (ea[k] > 0) {
-                    const float q = fadd(r[k], a7[k]);
-                    const float M = fmaxf(fabsf(r[k]), fabsf(q));
-                    const float d = fadd(fmul(M, 9.5367431640625e-07f), 1e-40f);
-                    if (fadd(q, d) < 0) {
-                        dead = true;
-                    } else if (!(fsub(q, d) > 0)) {
-                        float l = r[k];
-#pragma unroll
-                        for (int xx = 0; xx < 7; ++xx) l = fadd(l, ea[k]);
-                        dead = dead || !(l > thr[k]);
-                    }
-                }
-                r[k] = fadd(r[k], eb[k]);
-            }
-            if (!dead) live |= 1u << yy;
-        }
-    }
-
-    // Pass 2 -- the per-pixel walk of the live rows only (PixelShaderBase.h:68-92)
-    uint64_t mask = 0;
-    while (live) {
-        const int yy = ffs32(live) - 1;
-        live &= live - 1;
-        float v0 = e00[0], v1 = e00[1], v2 = e00[2];
-#pragma unroll
-        for (int sy = 0; sy < 7; ++sy)
-            if (sy < yy) { v0 = fadd(v0, eb[0]); v1 = fadd(v1, eb[1]); v2 = fadd(v2, eb[2]); }
-        uint32_t rowMask = 0;
-#pragma unroll
-        for (int xx = 0; xx < 8; ++xx) {
-            if (v0 > thr[0] && v1 > thr[1] && v2 > thr[2]) rowMask |= 1u << xx;
-            v0 = fadd(v0, ea[0]); v1 = fadd(v1, ea[1]); v2 = fadd(v2, ea[2]);
-        }
-        mask |= (uint64_t)rowMask << (yy * 8);
-    }
-    return mask;
-}
-#endif
 
 // Exact emptiness test of one 8x8 block (Block mode): for every edge the largest of the 64 per-pixel
 // chain values sits at pixel (a > 0 ? 7 : 0, b > 0 ? 7 : 0) -- the row-start chain is monotone in the

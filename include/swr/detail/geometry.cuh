@@ -516,7 +516,7 @@ SWR_D void publishGroup(const GeomArgs &g, Box16 box, uint32_t group, uint32_t c
 }
 
 #ifndef SWR_GEOM_MINB
-#define SWR_GEOM_MINB 1
+#define SWR_GEOM_MINB 4      // <= 64 registers: four 256-thread CTAs per SM (measured: 5 or 6 CTAs with spills are slower)
 #endif
 template <class VS>
 __global__ void __launch_bounds__(kGeomThreads, SWR_GEOM_MINB) geometryKernel(const GeomArgs g)

@@ -62,7 +62,7 @@ struct VSMvpNormalUv : public VertexShaderBase<VSMvpNormalUv> { // Box.cpp:65-87
     static const int PVarCount = 2;
     __device__ static void processVertex(VertexShaderInput in, VertexShaderOutput *out)
     {
-        const ObjVertex *d = static_cast<const ObjVertex *>(in[0]);
+        const ObjVertex v = fetchAttrib<ObjVertex>(in[0]), *d = &v;      // two 128-bit loads when the buffer allows (-1 % on C5)
         mvpTransform(uniforms<swr_stock_uniforms>().mvp, d->px, d->py, d->pz, out);
         out->avar[0] = d->nx; out->avar[1] = d->ny; out->avar[2] = d->nz;
         out->pvar[0] = d->u; out->pvar[1] = d->v;

@@ -151,6 +151,11 @@ struct swr_context {
     int lastTiles = 0;
     int ownedKey[5] = { 0, 0, 0, 0, 0 };   // {tile size, rank, world, width, height} of ownedIdx
     DevBuf stageAttrib[SWR_MAX_VERTEX_ATTRIBS];
+    // second staging set: streamed draws alternate, so the uploads of draw k+1 can run under the kernels of draw k
+    DevBuf stageIdxB, stageAttribB[SWR_MAX_VERTEX_ATTRIBS];
+    cudaEvent_t stageFree[2] = { nullptr, nullptr };   // recorded after the last kernel of the draw that last read the set
+    bool stageUsed[2] = { false, false };
+    int stageSet = 0;
     uint32_t *hostFlags = nullptr;   // pinned: error flag read-back
     bool debugStream = false;
 
@@ -173,7 +178,8 @@ int setDevice(swr_context *c)
 size_t scratchBytes(const swr_context *c)
 {
     size_t n = c->sets[0].bytes() + c->sets[1].bytes() + c->dbgVerts.bytes + c->stageIdx.bytes + c->l2flush.bytes + c->ownedIdx.bytes;
-    for (int i = 0; i < SWR_MAX_VERTEX_ATTRIBS; ++i) n += c->stageAttrib[i].bytes;
+    for (int i = 0; i < SWR_MAX_VERTEX_ATTRIBS; ++i) n += c->stageAttrib[i].bytes + c->stageAttribB[i].bytes;
+    n += c->stageIdxB.bytes;
     return n;
 }
 
@@ -335,21 +341,27 @@ int drawCommon(swr_context *c, int drawMode, size_t count, const int32_t *indice
     if (streamIdx) {
         if (!c->copy) CUDA_TRY(cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking));
         hs = c->copy;
-        CUDA_TRY(cudaEventRecord(c->evDrawStart, c->stream));             // the staging buffers may still be read by earlier draws
-        CUDA_TRY(cudaStreamWaitEvent(hs, c->evDrawStart, 0));
+        c->stageSet ^= 1;                                                 // the other set than the previous streamed draw
     }
+    const int S = streamIdx ? c->stageSet : 0;
+    DevBuf &stageIdx = S ? c->stageIdxB : c->stageIdx;
+    DevBuf *stageAttrib = S ? c->stageAttribB : c->stageAttrib;
+    bool staged = false;
+    if (streamIdx && c->stageUsed[S]) CUDA_TRY(cudaStreamWaitEvent(hs, c->stageFree[S], 0));   // kernels of the draw that last read this set
     if (!isDevicePointer(indices)) {
-        if (int rc = c->stageIdx.reserve(count * sizeof(int32_t))) return rc;
-        if (!streamIdx) CUDA_TRY(cudaMemcpyAsync(c->stageIdx.ptr, indices, idxBytes, cudaMemcpyHostToDevice, gs));
-        devIndices = static_cast<const int32_t *>(c->stageIdx.ptr);
+        if (int rc = stageIdx.reserve(count * sizeof(int32_t))) return rc;
+        if (!streamIdx) CUDA_TRY(cudaMemcpyAsync(stageIdx.ptr, indices, idxBytes, cudaMemcpyHostToDevice, gs));
+        devIndices = static_cast<const int32_t *>(stageIdx.ptr);
+        staged = true;
     }
     if (rasterVerts) {
         const void *dv = rasterVerts;
         if (!isDevicePointer(rasterVerts)) {
             const size_t bytes = rasterVertCount * 144;
-            if (int rc = c->stageAttrib[0].reserve(bytes)) return rc;
-            CUDA_TRY(cudaMemcpyAsync(c->stageAttrib[0].ptr, rasterVerts, bytes, cudaMemcpyHostToDevice, gs));
-            dv = c->stageAttrib[0].ptr;
+            if (int rc = stageAttrib[0].reserve(bytes)) return rc;
+            CUDA_TRY(cudaMemcpyAsync(stageAttrib[0].ptr, rasterVerts, bytes, cudaMemcpyHostToDevice, gs));
+            dv = stageAttrib[0].ptr;
+            staged = true;
         }
         g.rasterVerts = dv;
     } else {
@@ -358,9 +370,10 @@ int drawCommon(swr_context *c, int drawMode, size_t count, const int32_t *indice
             const void *dp = a.ptr;
             if (!isDevicePointer(a.ptr)) {
                 if (a.bytes == 0) return fail(-9, "vertex attribute %d is host memory: its extent is required (bytes > 0)", i);
-                if (int rc = c->stageAttrib[i].reserve(a.bytes)) return rc;
-                CUDA_TRY(cudaMemcpyAsync(c->stageAttrib[i].ptr, a.ptr, a.bytes, cudaMemcpyHostToDevice, hs));
-                dp = c->stageAttrib[i].ptr;
+                if (int rc = stageAttrib[i].reserve(a.bytes)) return rc;
+                CUDA_TRY(cudaMemcpyAsync(stageAttrib[i].ptr, a.ptr, a.bytes, cudaMemcpyHostToDevice, hs));
+                dp = stageAttrib[i].ptr;
+                staged = true;
             }
             g.attribPtr[i] = dp;
             g.attribStride[i] = a.stride;
@@ -500,7 +513,7 @@ int drawCommon(swr_context *c, int drawMode, size_t count, const int32_t *indice
         size_t k = 0;
         for (size_t first = 0; first < nprims; first += passPrims, ++k) {
             const size_t n = std::min(passPrims, nprims - first);
-            CUDA_TRY(cudaMemcpyAsync(static_cast<int32_t *>(c->stageIdx.ptr) + first * per, indices + first * per, n * per * sizeof(int32_t),
+            CUDA_TRY(cudaMemcpyAsync(static_cast<int32_t *>(stageIdx.ptr) + first * per, indices + first * per, n * per * sizeof(int32_t),
                                      cudaMemcpyHostToDevice, hs));
             CUDA_TRY(cudaEventRecord(c->idxReady[k], hs));
         }
@@ -568,6 +581,10 @@ int drawCommon(swr_context *c, int drawMode, size_t count, const int32_t *indice
         c->passSeq++;
     }
     CUDA_TRY(cudaEventRecord(c->evTile1, c->stream));
+    if (staged) {
+        CUDA_TRY(cudaEventRecord(c->stageFree[S], c->stream));
+        c->stageUsed[S] = true;
+    }
     CUDA_TRY(cudaGetLastError());
     c->haveDrawEvents = true;
     c->lastDrawMode = drawMode;
@@ -602,7 +619,8 @@ int swr_create(swr_context **out, int cuda_device)
     cudaEvent_t *evs[] = { &c->evGeom0, &c->evGeom1, &c->evTile0, &c->evTile1, &c->evTimer0, &c->evTimer1 };
     for (cudaEvent_t *ev : evs)
         if (e == cudaSuccess) e = cudaEventCreate(ev);
-    cudaEvent_t *sync[] = { &c->evDrawStart, &c->sets[0].geomDone, &c->sets[0].tileDone, &c->sets[1].geomDone, &c->sets[1].tileDone };
+    cudaEvent_t *sync[] = { &c->evDrawStart, &c->sets[0].geomDone, &c->sets[0].tileDone, &c->sets[1].geomDone, &c->sets[1].tileDone,
+                            &c->stageFree[0], &c->stageFree[1] };
     for (cudaEvent_t *ev : sync)
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
     if (const char *env = getenv("SWR_PIPELINE")) c->pipeline = atoi(env) != 0;
@@ -625,14 +643,15 @@ void swr_destroy(swr_context *c)
     cudaSetDevice(c->device);
     if (c->aux) cudaStreamSynchronize(c->aux);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    DevBuf *bufs[] = { &c->dbgVerts, &c->stageIdx, &c->l2flush, &c->ownedIdx, &c->tileStats };
+    DevBuf *bufs[] = { &c->dbgVerts, &c->stageIdx, &c->stageIdxB, &c->l2flush, &c->ownedIdx, &c->tileStats };
     for (DevBuf *b : bufs) b->release();
+    for (int i = 0; i < SWR_MAX_VERTEX_ATTRIBS; ++i) c->stageAttribB[i].release();
     for (ScratchSet &ss : c->sets) ss.release();
     for (int i = 0; i < SWR_MAX_VERTEX_ATTRIBS; ++i) c->stageAttrib[i].release();
     for (auto &o : c->ipcOpened) cudaIpcCloseMemHandle(o.second);
     if (c->hostFlags) cudaFreeHost(c->hostFlags);
     cudaEvent_t evs[] = { c->evGeom0, c->evGeom1, c->evTile0, c->evTile1, c->evTimer0, c->evTimer1, c->evDrawStart,
-                          c->sets[0].geomDone, c->sets[0].tileDone, c->sets[1].geomDone, c->sets[1].tileDone };
+                          c->sets[0].geomDone, c->sets[0].tileDone, c->sets[1].geomDone, c->sets[1].tileDone, c->stageFree[0], c->stageFree[1] };
     for (cudaEvent_t ev : evs)
         if (ev) cudaEventDestroy(ev);
     for (cudaEvent_t ev : c->idxReady) cudaEventDestroy(ev);

@@ -1,0 +1,25 @@
+"""Small draws of every kind for compute-sanitizer (memcheck / racecheck / synccheck).
+usage: compute-sanitizer --tool racecheck python tools/sanitize_run.py"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from softwarerenderer_b200 import scenes as S  # noqa: E402
+from softwarerenderer_b200.api import SceneRenderer  # noqa: E402
+
+cases = [
+    S.config_c3(120, 100, 320, 200),                                   # tiny triangles, clipping, extras
+    S.config_c3(120, 100, 320, 200, raster_mode=S.RASTER_SPAN),
+    S.config_c0(320, 200, ntri=300, ps=S.PS_GOURAUD_DEPTH, raster_mode=S.RASTER_BLOCK),   # big triangles: pre-test + dense path
+    S.config_c4(60, 40, 320, 200),                                     # lines
+    S.config_c4(60, 40, 320, 200, draw_mode=S.DRAW_POINT),
+    S.config_c5(40, 30, 2, 320, 200, ps=S.PS_TEXTURED_ANISO),
+]
+for tile in (32, 64):
+    for sc in cases:
+        sr = SceneRenderer(sc.width, sc.height, tile_size=tile)
+        out = sr.render(sc)
+        print(tile, sc.name, out["fragments"], flush=True)
+        sr.close()
+print("sanitize run done")

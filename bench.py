@@ -304,10 +304,14 @@ def run_gpu_arm(args):
         if args.composite == "mirror":
             # fused composite: the tile kernel stores finished tiles into the peers' surfaces (CUDA IPC / NVLink);
             # per step only a one-word NCCL all-reduce remains, as the barrier
-            comp = TileMirror(r, api.RT_COLOR, targets[api.RT_COLOR].data_ptr(), rank, world, dev)
-            clear()
-            comp.barrier()
-        else:
+            try:
+                comp = TileMirror(r, api.RT_COLOR, targets[api.RT_COLOR].data_ptr(), rank, world, dev)
+                clear()
+                comp.barrier()
+            except RuntimeError as e:                 # raised on every rank together (see TileMirror)
+                print(f"[bench] {e}; using the NCCL all-gather composite", file=sys.stderr)
+                args.composite = "nccl"
+        if comp is None:
             comp = TileComposite(r, W, H, tile, rank, world, dev)
 
     # ---- fragments per draw (deterministic): summed over ranks

@@ -108,10 +108,32 @@ class TileMirror:
         import torch.distributed as dist
         from . import api
         self.r, self.slot, self.rank, self.world = rasterizer, slot, rank, world
-        mine = api.ipc_handle(surface_ptr)
+        # every step that can fail is followed by a collective agreement, so that all ranks raise together
+        # (and the caller can fall back to TileComposite on all of them) instead of one rank leaving a collective
+        try:
+            mine = api.ipc_handle(surface_ptr)
+        except Exception as e:                       # e.g. memory that cannot be exported (cuMemMap-based allocators)
+            mine = ("error", str(e))
         handles = [None] * world
         dist.all_gather_object(handles, mine)
-        self.peers = [rasterizer.ipcOpen(h, off) for i, (h, off) in enumerate(handles) if i != rank]
+        bad = [h for h in handles if h[0] == "error"]
+        if bad:
+            raise RuntimeError(f"TileMirror: a surface cannot be exported over CUDA IPC: {bad[0][1]}")
+        self.peers = []
+        err = None
+        try:
+            for i, (h, off) in enumerate(handles):
+                if i != rank:
+                    self.peers.append(rasterizer.ipcOpen(h, off))
+        except Exception as e:
+            err = e
+        ok = torch.tensor([0 if err else 1], dtype=torch.int32, device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            for p in self.peers:
+                rasterizer.ipcClose(p)
+            self.peers = []
+            raise RuntimeError(f"TileMirror: a peer surface cannot be mapped: {err}")
         rasterizer.setTileMirrors(slot, self.peers)
         self._token = torch.zeros(1, dtype=torch.int32, device=device)
 

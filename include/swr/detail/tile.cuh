@@ -733,9 +733,18 @@ __global__ void __launch_bounds__(kTileThreads, SWR_TILE_MINB) tileKernel(const 
                         const uint32_t oex = __shfl_sync(0xffffffffu, fex, ol);
                         const int bit = fvalid ? nthSetBit64(om, (int)(f - oex)) : 0;
                         // fragments of different primitives on the same pixel run in emission order
-                        const int first = __shfl_sync(0xffffffffu, ol, 0);
+                        // (skipped when the round holds one primitive only, or -- the usual case on a mesh -- when the
+                        // round's pixels are provably all different: the OR of the lanes' one-hot pixel masks has as
+                        // many bits as there are fragments)
                         int rank = 0, maxRank = 0;
-                        if (!__all_sync(0xffffffffu, !fvalid || ol == first)) {
+                        const int first = __shfl_sync(0xffffffffu, ol, 0);
+                        bool clash = !__all_sync(0xffffffffu, !fvalid || ol == first);
+                        if (clash) {
+                            const uint32_t oneLo = (fvalid && bit < 32) ? 1u << bit : 0u, oneHi = (fvalid && bit >= 32) ? 1u << (bit - 32) : 0u;
+                            const int distinct = __popc(__reduce_or_sync(0xffffffffu, oneLo)) + __popc(__reduce_or_sync(0xffffffffu, oneHi));
+                            clash = distinct != (int)min(32u, totalF - fbase);
+                        }
+                        if (clash) {
                             const uint32_t peers = __match_any_sync(0xffffffffu, fvalid ? bit : 64 + lane);
                             rank = __popc(peers & ((1u << lane) - 1u));
                             maxRank = __reduce_max_sync(0xffffffffu, rank);

@@ -260,18 +260,45 @@ def run_gpu_arm(args):
         if comp is not None:
             comp.run(api.RT_COLOR)
 
-    repl = ReplicatedUpload([scene.vertices, scene.indices], rank, world, dev) if world > 1 else None
+    # N > 1: every rank uploads 1/N of the geometry over its own PCIe link and an NCCL all-gather replicates it.
+    # Two buffers alternate and the upload of step k+1 (on a second stream and its own process group) runs
+    # under the draw of step k; every timed step still contains exactly one upload, one draw and one read-back.
+    repl = None
+    if world > 1:
+        up_group = dist.new_group(ranks=list(range(world)))
+        up_stream = torch.cuda.Stream(device=dev)
+        repl = [ReplicatedUpload([scene.vertices, scene.indices], rank, world, dev, group=up_group) for _ in range(2)]
+        up_ready = [torch.cuda.Event(), torch.cuda.Event()]
+        up_free = [torch.cuda.Event(), torch.cuda.Event()]
+        up_state = {"k": 0, "ptrs": [None, None], "drawn": [False, False]}
+
+        def enqueue_upload(slot):
+            with torch.cuda.stream(up_stream):
+                if up_state["drawn"][slot]:
+                    up_stream.wait_event(up_free[slot])          # the draw that last read this buffer is done
+                up_state["ptrs"][slot] = repl[slot].run()
+                up_ready[slot].record(up_stream)
 
     def step_e2e():
         if world == 1:
             v.setVertexAttribPointer(0, scene.stride, h_vert)      # host pointers: staged H2D by the library
             v.drawElements(scene.draw_mode, count, h_idx, wait=False)
         else:
-            # every rank uploads 1/N of the geometry over its own PCIe link; NCCL all-gather replicates it
-            pv, pi = repl.run()
+            slot = up_state["k"] & 1
+            if up_state["ptrs"][slot] is None:
+                enqueue_upload(slot)                              # first step only: nothing was started ahead
+            if args.pipeline_upload:
+                enqueue_upload(slot ^ 1)                          # the next step's geometry, under this step's draw
+            stream.wait_event(up_ready[slot])
+            pv, pi = up_state["ptrs"][slot]
             v.setVertexAttribPointer(0, scene.stride, pv, nbytes=scene.vertices.nbytes)
             v.drawElements(scene.draw_mode, count, pi, wait=False)
             comp.run(api.RT_COLOR)
+            up_free[slot].record(stream)
+            up_state["drawn"][slot] = True
+            if not args.pipeline_upload:
+                up_state["ptrs"][slot] = None                     # the next step uploads for itself
+            up_state["k"] += 1
         if rank == 0:
             h_color.copy_(targets[api.RT_COLOR], non_blocking=True)  # D2H of the step's result (the composed frame)
 
@@ -395,7 +422,7 @@ def run_gpu_arm(args):
                          "draw": {"algorithmic_bytes": geom_b + frag_b / world, "achieved": ach_draw, "frac": ach_draw / peak,
                                   "distinct_vertices": v_ref}},
             "e2e": {"value": fragments / (ms_e2e / args.steps * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
-                    "h2d_bytes_per_step": int(scene.vertices.nbytes + scene.indices.nbytes) if world == 1 else int(repl.h2d_bytes * world),
+                    "h2d_bytes_per_step": int(scene.vertices.nbytes + scene.indices.nbytes) if world == 1 else int(repl[0].h2d_bytes * world),
                     "d2h_bytes_per_step": int(W * H * 4),
                     "path": "host buffers -> swr_draw_elements (staged by the library, indices streamed pass by pass) -> frame to host" if world == 1 else
                             f"each rank uploads 1/{world} of the geometry, NCCL all-gather replicates it, draw + composite, rank 0 reads the frame"},
@@ -418,6 +445,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3")
+    ap.add_argument("--pipeline-upload", type=int, default=1, help="N>1 end-to-end leg: upload step k+1 under the draw of step k")
     ap.add_argument("--composite", default="mirror", choices=["mirror", "nccl"],
                     help="N>1: fused peer stores from the tile kernel (default) or pack + NCCL all-gather + unpack")
     ap.add_argument("--tile", type=int, default=0)

@@ -157,9 +157,10 @@ class ReplicatedUpload:
     copies only 1/world of the bytes over its own PCIe link, then one NCCL all-gather over NVLink gives every
     rank the whole buffer.  Several arrays are packed into one byte buffer (256-byte aligned sections)."""
 
-    def __init__(self, arrays, rank: int, world: int, device):
+    def __init__(self, arrays, rank: int, world: int, device, group=None):
         import numpy as np
         import torch
+        self.group = group                              # a process group of its own lets the gather overlap other collectives
         self.offsets = []
         total = 0
         for a in arrays:
@@ -181,6 +182,6 @@ class ReplicatedUpload:
         """Enqueue on torch's current stream; returns the device address of each array."""
         import torch.distributed as dist
         self.slice_dev.copy_(self.slice_host, non_blocking=True)
-        dist.all_gather_into_tensor(self.full, self.slice_dev)
+        dist.all_gather_into_tensor(self.full, self.slice_dev, group=self.group)
         base = self.full.data_ptr()
         return [base + off for off in self.offsets]

@@ -78,6 +78,30 @@ def test_benchmark_full_known_answers(renderers):
             assert (zlib.crc32(got[k].view(np.uint8).tobytes()) & 0xFFFFFFFF) == ka[f"benchmark_full_{name}"]["crc_" + k], f"{name}:{k}"
 
 
+@pytest.mark.parametrize("name", ["c2", "c3"])
+def test_baseline_configs_at_full_size(oracle, name):
+    """BASELINE.json configs[1] (1M-triangle grid, 1080p, Gouraud + depth test) and configs[2] (10M tiny triangles,
+    4K, clipping + CW culling) at their full sizes, device-resident inputs as in the benchmark: colour and depth
+    buffers and the fragment count identical to the reference build (the restatement when it is absent)."""
+    from softwarerenderer_b200.api import SceneRenderer
+    scene = S.config_c2() if name == "c2" else S.config_c3()
+    want = oracle.run(scene, "ref" if oracle.have_ref() else "oracle")
+    for tile in (32, 64):                                    # size-independent property: the tile size never shows
+        sr = SceneRenderer(scene.width, scene.height, tile_size=tile)
+        vb, ib = sr.r.alloc(scene.vertices.nbytes), sr.r.alloc(scene.indices.nbytes)
+        sr.r.upload(vb, scene.vertices)
+        sr.r.upload(ib, scene.indices)
+        sr.targets.clear()
+        sr.r.resetStats()
+        sr.draw(scene, vertices=vb, indices=ib)
+        got = sr.targets.download()
+        assert int(sr.r.stats().fragments) == want["fragments"], (name, tile)
+        assert not common.diff_buffers(got, want, ("color", "depth")), (name, tile)
+        sr.r.free(vb)
+        sr.r.free(ib)
+        sr.close()
+
+
 def test_empty_and_ragged_counts(oracle, renderers):
     base = S.config_c0(ps=S.PS_COUNT_ID, ntri=1025)
     r = renderers(640, 480)

@@ -47,8 +47,14 @@ namespace detail {
 #endif
 constexpr int kQueue = SWR_QUEUE;    // primitives per flush
 constexpr int kItems = SWR_ITEMS;    // (primitive, block) items per flush
-constexpr int kChunkList = 1024;
-constexpr int kGroupList = 4096;
+#ifndef SWR_CHUNK_LIST
+#define SWR_CHUNK_LIST 1024
+#endif
+#ifndef SWR_GROUP_LIST
+#define SWR_GROUP_LIST 4096
+#endif
+constexpr int kChunkList = SWR_CHUNK_LIST;
+constexpr int kGroupList = SWR_GROUP_LIST;    // >= the per-tile list capacity of the binning pass (runtime.cu)
 constexpr int kTileWarps = kTileThreads / 32;
 constexpr int kPruneMax = 16;        // primitives with at most this many (primitive, block) items get the emptiness pre-test
 static_assert(2 * kTileThreads >= kQueue, "the item re-indexing scan handles two queue entries per thread");

@@ -113,6 +113,16 @@ public:
     void setUniforms(const void *data, size_t bytes) { detail::check(swr_set_uniforms(m_ctx, data, bytes), "setUniforms"); }
     /// Wait for all enqueued draws.
     void finish() const { detail::check(swr_finish(m_ctx), "finish"); }
+    /// Multi-GPU, one process per GPU (sort-first): this context shades the screen tiles of `rank` out of `world`.
+    void setTilePartition(int rank, int world) { detail::check(swr_set_tile_partition(m_ctx, rank, world), "setTilePartition"); }
+    /// ... and stores every finished tile of `slot` also into `count` peer surfaces (mapped with swr_ipc_open): the
+    /// composite then needs no pass of its own, only a cross-rank barrier after the draws (see swr_b200.h).
+    void setTileMirrors(int slot, int count, void *const *surfaces)
+    {
+        detail::check(swr_set_tile_mirrors(m_ctx, slot, count, surfaces), "setTileMirrors");
+    }
+    /// Enqueue on a caller-owned CUDA stream (nullptr: the context's own).
+    void setStream(void *cudaStream) { detail::check(swr_set_stream(m_ctx, cudaStream), "setStream"); }
     swr_context *context() const { return m_ctx; }
 
 private:

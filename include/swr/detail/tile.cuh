@@ -123,6 +123,11 @@ SWR_D bool boxOverlaps(const Box16 b, int X0, int Y0, int X1, int Y1)
     return b.x0 <= b.x1 && b.x0 <= X1 && b.x1 >= X0 && b.y0 <= Y1 && b.y1 >= Y0;
 }
 
+// li / nx for 0 <= li < 64, 1 <= nx <= 8 (item index -> block row of a primitive's block range) without the
+// ~25-instruction integer division: floor(li * ceil(256 / nx) / 256), exact on that range (checked exhaustively)
+static __constant__ uint16_t kCeil256Over[9] = { 0, 256, 128, 86, 64, 52, 43, 37, 32 };
+SWR_D int divSmall(int li, int nx) { return (li * (int)kCeil256Over[nx]) >> 8; }
+
 // position of the n-th (0-based) set bit: popcount binary search (the __fns intrinsic is a slow loop)
 SWR_D int nthSetBit32(uint32_t w, int n)
 {
@@ -198,7 +203,19 @@ SWR_HD uint64_t coverBlock(const float4 h0, const float4 h1, const float4 h2, in
             uint32_t rowMask = 0;
 #pragma unroll
             for (int xx = 0; xx < 8; ++xx) {
+#if defined(__CUDA_ARCH__)
+                // the three compares chained into one predicate + a predicated OR: 4 instructions per pixel
+                // (left to itself nvcc materialises every compare with SELs: ~7 per pixel)
+                asm("{\n\t.reg .pred p;\n\t"
+                    "setp.gt.f32 p, %1, %4;\n\t"
+                    "setp.gt.and.f32 p, %2, %5, p;\n\t"
+                    "setp.gt.and.f32 p, %3, %6, p;\n\t"
+                    "@p or.b32 %0, %0, %7;\n\t}"
+                    : "+r"(rowMask)
+                    : "f"(v0), "f"(v1), "f"(v2), "f"(thr[0]), "f"(thr[1]), "f"(thr[2]), "r"(1u << xx));
+#else
                 if (v0 > thr[0] && v1 > thr[1] && v2 > thr[2]) rowMask |= 1u << xx;
+#endif
                 v0 = fadd(v0, ea[0]); v1 = fadd(v1, ea[1]); v2 = fadd(v2, ea[2]);
             }
             mask |= (uint64_t)rowMask << (yy * 8);
@@ -561,8 +578,10 @@ __global__ void __launch_bounds__(kTileThreads, SWR_TILE_MINB) tileKernel(const 
                 if (!(f2u(h2.y) & kModeSpan)) {
                     const float4 h0 = t.head[(size_t)rec * 3], h1 = t.head[(size_t)rec * 3 + 1];
                     valid = 0;
-                    for (int li = 0; li < n; ++li)
-                        if (blockMayBeCovered(h0, h1, h2, X0 + (bx0 + li % nx) * 8, Y0 + (by0 + li / nx) * 8)) valid |= 1u << li;
+                    for (int li = 0; li < n; ++li) {
+                        const int ly = divSmall(li, nx), lx = li - ly * nx;
+                        if (blockMayBeCovered(h0, h1, h2, X0 + (bx0 + lx) * 8, Y0 + (by0 + ly) * 8)) valid |= 1u << li;
+                    }
                 }
             }
             qValid[q] = valid;
@@ -589,17 +608,19 @@ __global__ void __launch_bounds__(kTileThreads, SWR_TILE_MINB) tileKernel(const 
         if (timing) { const long long c = clock64(); cycA0 += c - cycMark; cycMark = c; }
         // A: one thread per (primitive, block) item
         for (uint32_t it = tid; it < nItems; it += kTileThreads) {
-            uint32_t lo = 0, hi = nQ;                        // largest q with qItem[q] <= it
-            while (hi - lo > 1) {
-                const uint32_t mid = (lo + hi) >> 1;
-                if (qItem[mid] <= it) lo = mid; else hi = mid;
+            uint32_t lo = 0;                                 // largest q < nQ with qItem[q] <= it (qItem[0] = 0)
+#pragma unroll
+            for (uint32_t step = kQueue / 2; step > 0; step >>= 1) {
+                const uint32_t mid = lo + step;
+                if (mid < nQ && qItem[mid] <= it) lo = mid;
             }
             const uint32_t q = lo, rec = qRec[q], rg = qRange[q];
             const int bx0 = rg & 0xff, by0 = (rg >> 8) & 0xff, nx = (int)((rg >> 16) & 0xff) - bx0 + 1;
             const int nAll = nx * ((int)(rg >> 24) - by0 + 1);
             const int k = (int)(it - qItem[q]);
             const int li = nAll <= kPruneMax ? nthSetBit32(qValid[q], k) : k;     // k-th surviving item -> block
-            const int bx = bx0 + li % nx, by = by0 + li / nx;
+            const int liy = divSmall(li, nx);
+            const int bx = bx0 + li - liy * nx, by = by0 + liy;
             const int gx = X0 + bx * 8, gy = Y0 + by * 8;
             uint64_t m;
             if (MODE == SWR_DRAW_TRIANGLE) {

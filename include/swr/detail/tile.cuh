@@ -347,45 +347,71 @@ SWR_HD void shadeTriangleFragment(const TileArgs &t, uint32_t rec, int gx, int g
         eq.e2.a = h1.z; eq.e2.b = h1.w; eq.e2.c = h2.x; eq.e2.tie = (flags & kTie2) != 0;
     }
 
-    auto chain = [&](const float a, const float b, const float c) __attribute__((always_inline)) -> float {
-        float v = fadd(fadd(fmul(a, xf), fmul(b, yf)), c);          // ParameterEquation::evaluate
+    // All planes walk the same steps, so the steps are the outer loop and up to kChainGroup planes the inner
+    // one: one step predicate serves the whole group (per plane on its own it is recomputed for every plane:
+    // 14 compares each).  Per plane the additions and their order are untouched.
+    constexpr int NPL = (TR::Z ? 1 : 0) + (TR::WP ? 1 : 0) + TR::NA + TR::NP;
+    constexpr int kChainGroup = 6;
+    const float4 *pl4 = reinterpret_cast<const float4 *>(pl);      // one 128-bit load per plane
+    float val[NPL > 0 ? NPL : 1];
+#pragma unroll
+    for (int g0 = 0; g0 < NPL; g0 += kChainGroup) {
+        float ca[kChainGroup], cb[kChainGroup], cv[kChainGroup];
+#pragma unroll
+        for (int i = 0; i < kChainGroup; ++i) {
+            if (g0 + i < NPL) {
+                const float4 q = pl4[g0 + i];
+                ca[i] = q.x; cb[i] = q.y;
+                cv[i] = fadd(fadd(fmul(q.x, xf), fmul(q.y, yf)), q.z);      // ParameterEquation::evaluate
+            }
+        }
         if (flags & kModeSpan) {
-            for (int s = 0; s < ncol; ++s) v = fadd(v, a);
+            for (int s = 0; s < ncol; ++s) {
+#pragma unroll
+                for (int i = 0; i < kChainGroup; ++i)
+                    if (g0 + i < NPL) cv[i] = fadd(cv[i], ca[i]);
+            }
         } else {
 #pragma unroll
-            for (int s = 0; s < 7; ++s) if (s < nrow) v = fadd(v, b);   // stepY
+            for (int s = 0; s < 7; ++s) {                                    // stepY
+                const bool on = s < nrow;
 #pragma unroll
-            for (int s = 0; s < 7; ++s) if (s < ncol) v = fadd(v, a);   // stepX
+                for (int i = 0; i < kChainGroup; ++i)
+                    if (g0 + i < NPL && on) cv[i] = fadd(cv[i], cb[i]);
+            }
+#pragma unroll
+            for (int s = 0; s < 7; ++s) {                                    // stepX
+                const bool on = s < ncol;
+#pragma unroll
+                for (int i = 0; i < kChainGroup; ++i)
+                    if (g0 + i < NPL && on) cv[i] = fadd(cv[i], ca[i]);
+            }
         }
-        return v;
-    };
+#pragma unroll
+        for (int i = 0; i < kChainGroup; ++i)
+            if (g0 + i < NPL) val[g0 + i] = cv[i];
+    }
 
-    // one 128-bit load per plane
-    const float4 *pl4 = reinterpret_cast<const float4 *>(pl);
     int o = 0;
     if (TR::Z) {
-        const float4 q = pl4[o++];
+        const float4 q = pl4[o];
         eq.z.a = q.x; eq.z.b = q.y; eq.z.c = q.z;
-        p.z = chain(q.x, q.y, q.z);
+        p.z = val[o++];
     }
     if (TR::WP) {
-        const float4 q = pl4[o++];
+        const float4 q = pl4[o];
         eq.invw.a = q.x; eq.invw.b = q.y; eq.invw.c = q.z;
-        p.invw = chain(q.x, q.y, q.z);
+        p.invw = val[o++];
         p.w = fdiv(1.0f, p.invw);
     }
     eq.avar.planes = pl + 4 * o;
 #pragma unroll
-    for (int i = 0; i < TR::NA; ++i) {
-        const float4 q = pl4[o + i];
-        p.avar[i] = chain(q.x, q.y, q.z);
-    }
+    for (int i = 0; i < TR::NA; ++i) p.avar[i] = val[o + i];
     o += TR::NA;
     eq.pvar.planes = pl + 4 * o;
 #pragma unroll
     for (int i = 0; i < TR::NP; ++i) {
-        const float4 q = pl4[o + i];
-        p.pvarTemp[i] = chain(q.x, q.y, q.z);
+        p.pvarTemp[i] = val[o + i];
         p.pvar[i] = fmul(p.pvarTemp[i], p.w);
     }
     p.equations = &eq;

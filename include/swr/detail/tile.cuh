@@ -58,6 +58,7 @@ constexpr int kGroupList = SWR_GROUP_LIST;    // >= the per-tile list capacity o
 constexpr int kTileWarps = kTileThreads / 32;
 constexpr int kPruneMax = 16;        // primitives with at most this many (primitive, block) items get the emptiness pre-test
 static_assert(2 * kTileThreads >= kQueue, "the item re-indexing scan handles two queue entries per thread");
+static_assert(4 * kTileThreads < (1 << 12) && 4 * 64 * kTileThreads < (1 << 20), "packing of the 32-bit record scan (count << 20 | items)");
 
 template <int TLOG, int NRT>
 struct TileSmem {
@@ -85,30 +86,34 @@ struct Ctl { uint32_t accQ, accItems; int nextBlock; };
 // Exclusive block scan of a packed (hi: count, lo: sum) pair.  ONE barrier: every warp publishes its
 // total, then each warp scans the (at most 32) warp totals for itself.  The scratch is double buffered,
 // so back-to-back calls need no trailing barrier (a warp can be at most one call behind the others).
-SWR_D uint64_t blockScan(uint64_t v, uint64_t &total, uint64_t *scratch, int &phase)
+template <class T>
+SWR_D T blockScanT(T v, T &total, uint64_t *scratch, int &phase)
 {
     static_assert(kTileWarps <= 32, "one lane per warp total");
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    uint64_t *s = scratch + phase * (kTileWarps + 1);
+    T *s = reinterpret_cast<T *>(scratch + phase * (kTileWarps + 1));
     phase ^= 1;
-    uint64_t incl = v;
+    T incl = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        uint64_t n = __shfl_up_sync(0xffffffffu, incl, o);
+        T n = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += n;
     }
     if (lane == 31) s[wid] = incl;
     __syncthreads();
-    const uint64_t w = lane < kTileWarps ? s[lane] : 0;
-    uint64_t wi = w;
+    const T w = lane < kTileWarps ? s[lane] : 0;
+    T wi = w;
 #pragma unroll
     for (int o = 1; o < kTileWarps; o <<= 1) {
-        uint64_t n = __shfl_up_sync(0xffffffffu, wi, o);
+        T n = __shfl_up_sync(0xffffffffu, wi, o);
         if (lane >= o) wi += n;
     }
     total = __shfl_sync(0xffffffffu, wi, kTileWarps - 1);
     return incl - v + __shfl_sync(0xffffffffu, wi - w, wid);
 }
+SWR_D uint64_t blockScan(uint64_t v, uint64_t &total, uint64_t *scratch, int &phase) { return blockScanT<uint64_t>(v, total, scratch, phase); }
+// 32-bit flavour (half the shuffles) for the steps whose packed pair fits: hi 12 bits count, lo 20 bits sum
+SWR_D uint32_t blockScan32(uint32_t v, uint32_t &total, uint64_t *scratch, int &phase) { return blockScanT<uint32_t>(v, total, scratch, phase); }
 
 #ifndef SWR_PREFETCH
 #define SWR_PREFETCH 7
@@ -190,15 +195,16 @@ SWR_HD uint64_t coverBlock(const float4 h0, const float4 h1, const float4 h2, in
     // row by row, exact row maxima from the full 7-add chains
     uint64_t mask = 0;
     float r0 = e00[0], r1 = e00[1], r2 = e00[2];
+    const bool up0 = ea[0] > 0, up1 = ea[1] > 0, up2 = ea[2] > 0;
 #pragma unroll 1
     for (int yy = 0; yy < 8; ++yy) {
         float l0 = r0, l1 = r1, l2 = r2;
 #pragma unroll
         for (int xx = 0; xx < 7; ++xx) { l0 = fadd(l0, ea[0]); l1 = fadd(l1, ea[1]); l2 = fadd(l2, ea[2]); }
-        const bool dead = (ea[0] <= 0 && !(r0 > thr[0])) || (ea[0] > 0 && !(l0 > thr[0])) ||
-                          (ea[1] <= 0 && !(r1 > thr[1])) || (ea[1] > 0 && !(l1 > thr[1])) ||
-                          (ea[2] <= 0 && !(r2 > thr[2])) || (ea[2] > 0 && !(l2 > thr[2]));
-        if (!dead) {
+        // the row's maximum per edge: last chain value for a > 0, first one otherwise (a NaN coefficient lands
+        // on the first value too, which is then the only one of the row that is not NaN: still exact)
+        const float m0 = up0 ? l0 : r0, m1 = up1 ? l1 : r1, m2 = up2 ? l2 : r2;
+        if (m0 > thr[0] && m1 > thr[1] && m2 > thr[2]) {
             float v0 = r0, v1 = r1, v2 = r2;
             uint32_t rowMask = 0;
 #pragma unroll
@@ -622,8 +628,8 @@ __global__ void __launch_bounds__(kTileThreads, SWR_TILE_MINB) tileKernel(const 
                 return n <= kPruneMax ? (uint32_t)__popc(qValid[q]) : (uint32_t)n;
             };
             const uint32_t c0 = itemCount(2 * tid), c1 = itemCount(2 * tid + 1);
-            uint64_t total;
-            const uint32_t ex = (uint32_t)blockScan((uint64_t)(c0 + c1), total, sScan, phase);
+            uint32_t total;
+            const uint32_t ex = blockScan32(c0 + c1, total, sScan, phase);
             if (2u * tid < nQ) qItem[2 * tid] = ex;
             if (2u * tid + 1 < nQ) qItem[2 * tid + 1] = ex + c0;
             nItems = (uint32_t)total;
@@ -859,11 +865,11 @@ __global__ void __launch_bounds__(kTileThreads, SWR_TILE_MINB) tileKernel(const 
                         }
                     }
                 }
-                uint64_t total;
-                const uint64_t ex = blockScan(((uint64_t)cnt << 32) | sum, total, sScan, phase);
-                const uint32_t totHit = (uint32_t)(total >> 32), totItems = (uint32_t)total;
+                uint32_t total;                              // packed: count (<= 2048 per step) << 20 | items (<= 2^17 per step)
+                const uint32_t ex = blockScan32((cnt << 20) | sum, total, sScan, phase);
+                const uint32_t totHit = total >> 20, totItems = total & 0xfffffu;
                 if (totHit == 0) break;
-                uint32_t eh = (uint32_t)(ex >> 32), ei = (uint32_t)ex;
+                uint32_t eh = ex >> 20, ei = ex & 0xfffffu;
                 const bool fitsAll = nQ + totHit <= kQueue && nItems + totItems <= kItems;
                 uint32_t nAcc = 0, accItems = 0;
 #pragma unroll
@@ -982,8 +988,8 @@ __global__ void __launch_bounds__(kTileThreads, SWR_TILE_MINB) tileKernel(const 
                     for (int k = 0; k < 4; ++k)
                         if (((valid >> k) & 1u) && boxOverlaps(gb[k], X0, Y0, X1, Y1)) hits |= 1u << k;
                 }
-                uint64_t tot2;
-                uint32_t e2 = nGroup + (uint32_t)blockScan((uint64_t)__popc(hits), tot2, sScan, phase);
+                uint32_t tot2;
+                uint32_t e2 = nGroup + blockScan32((uint32_t)__popc(hits), tot2, sScan, phase);
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                     if ((hits >> k) & 1u) gList[e2++] = grp[k];

@@ -16,7 +16,7 @@ struct EdgeEquation {
         using namespace detail;
         a = fsub(v0y, v1y);
         b = fsub(v1x, v0x);
-        c = fdiv(-fadd(fmul(a, fadd(v0x, v1x)), fmul(b, fadd(v0y, v1y))), 2.0f);
+        c = fmul(-fadd(fmul(a, fadd(v0x, v1x)), fmul(b, fadd(v0y, v1y))), 0.5f);   // x / 2 == x * 0.5 to the bit (EdgeEquation.h:44 divides by 2)
         tie = a != 0 ? a > 0 : b > 0;
     }
     SWR_HD void init(const RasterizerVertex &v0, const RasterizerVertex &v1) { init(v0.x, v0.y, v1.x, v1.y); }

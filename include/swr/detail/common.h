@@ -50,6 +50,7 @@ SWR_HD float fmul(float a, float b) { return __fmul_rn(a, b); }
 SWR_HD float fadd(float a, float b) { return __fadd_rn(a, b); }
 SWR_HD float fsub(float a, float b) { return __fsub_rn(a, b); }
 SWR_HD float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+SWR_HD float frcp(float a) { return __frcp_rn(a); }           // == 1.0f / a, correctly rounded: same bits as fdiv(1.0f, a)
 SWR_HD int f2i(float a) { return __float2int_rz(a); }
 SWR_HD float i2f(int a) { return __int2float_rn(a); }
 #else
@@ -58,6 +59,7 @@ SWR_HD float fmul(float a, float b) { return a * b; }
 SWR_HD float fadd(float a, float b) { return a + b; }
 SWR_HD float fsub(float a, float b) { return a - b; }
 SWR_HD float fdiv(float a, float b) { return a / b; }
+SWR_HD float frcp(float a) { return 1.0f / a; }
 SWR_HD int f2i(float a) { return (int)a; }
 SWR_HD float i2f(int a) { return (float)a; }
 #endif

@@ -124,7 +124,7 @@ SWR_HD int clipTriangle(CVert<NA, NP> *bufA, CVert<NA, NP> *bufB, int mask, CVer
 template <int NA, int NP>
 SWR_HD void toScreen(const GeomArgs &g, CVert<NA, NP> &v)
 {
-    const float invW = fdiv(1.0f, v.w);
+    const float invW = frcp(v.w);
     v.x = fmul(v.x, invW);
     v.y = fmul(v.y, invW);
     v.z = fmul(v.z, invW);
@@ -315,7 +315,7 @@ SWR_HD Box16 emitScreenTriangle(const GeomArgs &g, uint32_t rec, uint32_t ordina
 
     // interpolation planes (TriangleEquations.h:59-70), order: z?, invw?, avar[nA], pvar[nP]; one float4 each
     float4 *pp4 = reinterpret_cast<float4 *>(g.params + (size_t)rec * g.paramStride);
-    const float factor = fdiv(1.0f, area2);
+    const float factor = frcp(area2);
     ParameterEquation pe;
     if (g.useZ) {
         pe.init(v0->z, v1->z, v2->z, e0, e1, e2, factor);
@@ -323,7 +323,7 @@ SWR_HD Box16 emitScreenTriangle(const GeomArgs &g, uint32_t rec, uint32_t ordina
     }
     float iw0 = 0.0f, iw1 = 0.0f, iw2 = 0.0f;
     if (g.useW || g.nP > 0) {
-        iw0 = fdiv(1.0f, v0->w); iw1 = fdiv(1.0f, v1->w); iw2 = fdiv(1.0f, v2->w);
+        iw0 = frcp(v0->w); iw1 = frcp(v1->w); iw2 = frcp(v2->w);
         pe.init(iw0, iw1, iw2, e0, e1, e2, factor);
         *pp4++ = mkf4(pe.a, pe.b, pe.c, 0.0f);
     }
@@ -489,14 +489,9 @@ SWR_D void shadeVertex(const GeomArgs &g, int index, CVert<VS::AVarCount, VS::PV
 // tile x chunk bitmap.
 SWR_D void publishGroup(const GeomArgs &g, Box16 box, uint32_t group, uint32_t chunk)
 {
-    int x0 = box.x0, y0 = box.y0, x1 = box.x1, y1 = box.y1;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        x0 = min(x0, __shfl_xor_sync(0xffffffffu, x0, o));
-        y0 = min(y0, __shfl_xor_sync(0xffffffffu, y0, o));
-        x1 = max(x1, __shfl_xor_sync(0xffffffffu, x1, o));
-        y1 = max(y1, __shfl_xor_sync(0xffffffffu, y1, o));
-    }
+    // warp-wide min / max in one instruction each (redux.sync) instead of four 5-step shuffle trees
+    const int x0 = __reduce_min_sync(0xffffffffu, (int)box.x0), y0 = __reduce_min_sync(0xffffffffu, (int)box.y0);
+    const int x1 = __reduce_max_sync(0xffffffffu, (int)box.x1), y1 = __reduce_max_sync(0xffffffffu, (int)box.y1);
     const int lane = threadIdx.x & 31;
     if (lane == 0) {
         Box16 u; u.x0 = (int16_t)x0; u.y0 = (int16_t)y0; u.x1 = (int16_t)x1; u.y1 = (int16_t)y1;
@@ -508,8 +503,9 @@ SWR_D void publishGroup(const GeomArgs &g, Box16 box, uint32_t group, uint32_t c
     if (tx0 > tx1 || ty0 > ty1) return;
     const int nx = tx1 - tx0 + 1, nt = nx * (ty1 - ty0 + 1);
     const uint32_t bit = 1u << (chunk & 31);
+    const bool oneRow = ty0 == ty1, oneCol = tx0 == tx1;     // the usual shapes: no integer division for them
     for (int i = lane; i < nt; i += 32) {
-        const int tile = (ty0 + i / nx) * g.tilesX + tx0 + i % nx;
+        const int tile = oneRow ? ty0 * g.tilesX + tx0 + i : oneCol ? (ty0 + i) * g.tilesX + tx0 : (ty0 + i / nx) * g.tilesX + tx0 + i % nx;
         uint32_t *wp = g.tilemap + (size_t)tile * g.chunkWords + (chunk >> 5);
         if (!(*(volatile uint32_t *)wp & bit)) atomicOr(wp, bit);
     }

@@ -408,7 +408,7 @@ SWR_HD void shadeTriangleFragment(const TileArgs &t, uint32_t rec, int gx, int g
         const float4 q = pl4[o];
         eq.invw.a = q.x; eq.invw.b = q.y; eq.invw.c = q.z;
         p.invw = val[o++];
-        p.w = fdiv(1.0f, p.invw);
+        p.w = frcp(p.invw);
     }
     eq.avar.planes = pl + 4 * o;
 #pragma unroll
@@ -451,7 +451,7 @@ SWR_HD int shadeLineFragments(const TileArgs &t, uint32_t rec, int px, int py, P
             p.x = px;
             p.y = py;
             if (TR::Z) p.z = z;
-            if (TR::W) { p.w = w; p.invw = fdiv(1.0f, w); }
+            if (TR::W) { p.w = w; p.invw = frcp(w); }
 #pragma unroll
             for (int i = 0; i < TR::NA; ++i) p.avar[i] = av[i];
 #pragma unroll
@@ -484,7 +484,7 @@ SWR_HD void shadePointFragment(const TileArgs &t, uint32_t rec, int px, int py, 
     p.y = py;
     int o = 0;
     if (TR::Z) { p.z = pl[o]; o += 1; }
-    if (TR::W) { p.w = pl[o]; p.invw = fdiv(1.0f, p.w); o += 1; }
+    if (TR::W) { p.w = pl[o]; p.invw = frcp(p.w); o += 1; }
 #pragma unroll
     for (int i = 0; i < TR::NA; ++i) p.avar[i] = pl[o + i];
     o += TR::NA;

@@ -51,11 +51,11 @@ def load_peaks():
 
 def ncu_traffic(workload: str, tile: int, world: int):
     """dram__bytes_read.sum + dram__bytes_write.sum of the tile kernel from the committed ncu --set full capture
-    (profiles/r01c_summary.json: C3, 64-pixel tiles, one GPU); None for any other configuration."""
+    (profiles/r01d_summary.json: C3, 64-pixel tiles, one GPU); None for any other configuration."""
     if workload != "c3" or tile != 64 or world != 1:
         return None
     try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "r01c_summary.json")))["tile"]
+        d = json.load(open(os.path.join(ROOT, "profiles", "r01d_summary.json")))["tile"]
 
         def mb(v):
             num, unit = v.split()[:2]

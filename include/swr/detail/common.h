@@ -120,6 +120,7 @@ struct GeomArgs {
     uint32_t *errorFlag;
     float *dbgVerts;                 // optional: 12 floats per record (3 x xyzw, screen space)
     int32_t rank, world;             // sort-first: records that touch no tile owned by this rank are dropped
+    int32_t noTightBox;              // debug: keep the reference's 8-aligned block box instead of the certified pixel bounds
 };
 
 // Arguments of the tile kernel.

@@ -244,6 +244,78 @@ SWR_HD uint32_t f2u(float f)
 #endif
 }
 
+// Certified pixel bounds of a Block-mode triangle.  The reference visits every 8x8 block of the truncated,
+// 8-aligned bounding box (Rasterizer.h:234-255) and tests each pixel with incremental fp32 chains
+// (EdgeData.h:37-66); most of those pixels can be excluded up front without changing a single result.
+// With u = 2^-24 (half an ulp, relative) and everything below in REAL arithmetic on the stored fp32 coefficients:
+//
+//   (1) every value the reference compares for edge k at a pixel -- the per-pixel chain value as well as the four
+//       block-corner values of Rasterizer.h:272-275 -- is E_k(centre) = a_k x + b_k y + c_k plus at most 18
+//       roundings of values bounded by M_k = |a_k| X + |b_k| Y + |c_k| (X, Y = the box's far pixel edge), so it
+//       differs from E_k by less than 32 u M_k.  A pixel (or block corner) that passes test k has E_k > -32 u M_k.
+//   (2) the stored line misses the two vertices p, q it was built from (EdgeEquation.h:38-46) by at most
+//       |E_k(p)|, |E_k(q)| <= 2u (|a||b| + |a|(|p.x|+|q.x|) + |b|(|p.y|+|q.y|))   (a, b: one rounding each;
+//       c: three roundings of the two products and their sum).
+//   (3) so every fragment lies in the triangle spanned by the lines E_k = -32 u M_k, whose corner at the edges
+//       i, j is displaced from the vertex the two edges share by a vector s with |n_i.s| <= D_i, |n_j.s| <= D_j,
+//       D_k = (1) + (2); Cramer's rule bounds |s.x| <= (D_i |b_j| + D_j |b_i|) / det, |s.y| likewise, with
+//       det = a_i b_j - a_j b_i > 0 taken at its fp32 lower bound.
+// The bounds are the vertices' bounding box grown by the largest displacement and 0.02 pixel (which covers the
+// fp32 roundings of this function itself).  Pixels outside can pass no edge test of the reference and no block they
+// lie in can be classified "fully covered", so restricting binning and coverage to the bounds is exact.  Returns
+// false when nothing can be certified (degenerate / non-finite coefficients): the caller keeps the block box.
+SWR_HD float fabs32(float v) { return v < 0 ? -v : v; }
+
+SWR_HD bool tightPixelBounds(const EdgeEquation &e0, const EdgeEquation &e1, const EdgeEquation &e2,
+                             float v0x, float v0y, float v1x, float v1y, float v2x, float v2y,
+                             float fminX, float fminY, float fmaxX, float fmaxY,
+                             int bx0, int by0, int bx1, int by1, int &x0, int &y0, int &x1, int &y1)
+{
+    const float X = i2f(bx1 + 1), Y = i2f(by1 + 1);
+    const float a[3] = { fabs32(e0.a), fabs32(e1.a), fabs32(e2.a) };
+    const float b[3] = { fabs32(e0.b), fabs32(e1.b), fabs32(e2.b) };
+    const float c[3] = { fabs32(e0.c), fabs32(e1.c), fabs32(e2.c) };
+    // end points of the edges: e0 = (v1, v2), e1 = (v2, v0), e2 = (v0, v1)   (emitScreenTriangle)
+    const float sx[3] = { fabs32(v1x) + fabs32(v2x), fabs32(v2x) + fabs32(v0x), fabs32(v0x) + fabs32(v1x) };
+    const float sy[3] = { fabs32(v1y) + fabs32(v2y), fabs32(v2y) + fabs32(v0y), fabs32(v0y) + fabs32(v1y) };
+    const float kEval = 1.0f / 524288.0f;        // 32 u = 2^-19
+    const float kLine = 1.0f / 8388608.0f;       // 2 u = 2^-23
+    const float kUp = 1.0f + 1.0f / 65536.0f;    // absorbs the roundings of the bound's own arithmetic
+    float D[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float M = a[k] * X + b[k] * Y + c[k];
+        const float L = a[k] * b[k] + a[k] * sx[k] + b[k] * sy[k];
+        D[k] = (M * kEval + L * kLine) * kUp + 1e-30f;
+    }
+    const float sa[3] = { e0.a, e1.a, e2.a }, sb[3] = { e0.b, e1.b, e2.b };
+    float dx = 0.0f, dy = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const int j = i == 2 ? 0 : i + 1;
+        const float p1 = sa[i] * sb[j], p2 = sa[j] * sb[i];
+        const float det = (p1 - p2) - (fabs32(p1) + fabs32(p2)) * (1.0f / 4194304.0f);     // lower bound: - 4u (|p1| + |p2|)
+        if (!(det > 1e-30f)) return false;
+        const float r = kUp / det;
+        const float ddx = (D[i] * b[j] + D[j] * b[i]) * r, ddy = (D[i] * a[j] + D[j] * a[i]) * r;
+        dx = ddx > dx ? ddx : dx;
+        dy = ddy > dy ? ddy : dy;
+    }
+    if (!(dx < 64.0f) || !(dy < 64.0f)) return false;            // (also catches NaN) nothing worth certifying
+    // pixel p has its centre at p + 0.5: it can hold a fragment only if  min - d <= p + 0.5 <= max + d
+    const float lx0 = fminX - dx - 0.52f, ly0 = fminY - dy - 0.52f, lx1 = fmaxX + dx - 0.48f, ly1 = fmaxY + dy - 0.48f;
+    if (!(lx0 > -1e9f) || !(ly0 > -1e9f) || !(lx1 < 1e9f) || !(ly1 < 1e9f)) return false;
+    // ceil / floor, clamped to the reference's block box [bx0, bx1] x [by0, by1]
+    const float fx0 = i2f(bx0), fy0 = i2f(by0), fx1 = i2f(bx1), fy1 = i2f(by1);
+    int px0 = bx0, py0 = by0, px1 = bx1, py1 = by1;
+    if (lx0 > fx0) { if (lx0 > fx1) px0 = bx1 + 1; else { const int t = f2i(lx0); px0 = i2f(t) < lx0 ? t + 1 : t; } }
+    if (ly0 > fy0) { if (ly0 > fy1) py0 = by1 + 1; else { const int t = f2i(ly0); py0 = i2f(t) < ly0 ? t + 1 : t; } }
+    if (lx1 < fx1) { if (lx1 < fx0) px1 = bx0 - 1; else px1 = f2i(lx1); }
+    if (ly1 < fy1) { if (ly1 < fy0) py1 = by0 - 1; else py1 = f2i(ly1); }
+    x0 = px0; y0 = py0; x1 = px1; y1 = py1;
+    return true;
+}
+
 // Screen-space triangle -> record `rec`.  Cull / re-orient (VertexProcessor.cpp:319-345), setup
 // (TriangleEquations.h:47-71), footprint (Rasterizer.h:234-255 or the span halves).  Returns the
 // footprint box (dead when the triangle is dropped anywhere on the way).
@@ -300,7 +372,11 @@ SWR_HD Box16 emitScreenTriangle(const GeomArgs &g, uint32_t rec, uint32_t ordina
         minX &= ~7; maxX &= ~7; minY &= ~7; maxY &= ~7;
         const int stepsX = (maxX - minX) / 8 + 1, stepsY = (maxY - minY) / 8 + 1;
         if (stepsX <= 0 || stepsY <= 0) return deadBox();            // reference loop does not run (P23 aside)
-        box = makeBox(minX, minY, maxX + 7, maxY + 7);
+        int tx0 = minX, ty0 = minY, tx1 = maxX + 7, ty1 = maxY + 7;
+        if (!g.noTightBox && minX >= 0 && minY >= 0 && maxX + 7 <= 32767 && maxY + 7 <= 32767)
+            tightPixelBounds(e0, e1, e2, v0->x, v0->y, v1->x, v1->y, v2->x, v2->y, fminX, fminY, fmaxX, fmaxY,
+                             minX, minY, maxX + 7, maxY + 7, tx0, ty0, tx1, ty1);
+        box = makeBox(tx0, ty0, tx1, ty1);                            // a sub-pixel triangle that misses every pixel centre dies here
         if (box.x0 > box.x1) return box;
     }
 

@@ -123,6 +123,13 @@ SWR_D uint32_t blockScan32(uint32_t v, uint32_t &total, uint64_t *scratch, int &
 #endif
 SWR_D void prefetchL2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+// qRange: a queued primitive's pixel bounds inside the tile, 6 bits each (tiles are at most 64 pixels wide)
+SWR_HD uint32_t packRange(int lx0, int ly0, int lx1, int ly1) { return (uint32_t)lx0 | ((uint32_t)ly0 << 6) | ((uint32_t)lx1 << 12) | ((uint32_t)ly1 << 18); }
+SWR_HD int rangeBx0(uint32_t rg) { return (int)((rg >> 3) & 7u); }
+SWR_HD int rangeBy0(uint32_t rg) { return (int)((rg >> 9) & 7u); }
+SWR_HD int rangeBx1(uint32_t rg) { return (int)((rg >> 15) & 7u); }
+SWR_HD int rangeBy1(uint32_t rg) { return (int)((rg >> 21) & 7u); }
+
 SWR_D bool boxOverlaps(const Box16 b, int X0, int Y0, int X1, int Y1)
 {
     return b.x0 <= b.x1 && b.x0 <= X1 && b.x1 >= X0 && b.y0 <= Y1 && b.y1 >= Y0;
@@ -162,25 +169,31 @@ SWR_D int nthSetBit64(uint64_t m, int n)
 // v, v+a, (v+a)+a, ... is monotone (an fp32 add of a constant is monotone), so its maximum is the
 // first value when a <= 0 and the last one when a > 0; if that maximum fails an edge's test no
 // pixel of the row can pass, and the 8 x 3 per-pixel tests are skipped.
-SWR_HD uint64_t coverBlock(const float4 h0, const float4 h1, const float4 h2, int gx, int gy)
+struct BlockEdges { float ea[3], eb[3], thr[3], e00[3]; };
+constexpr int kNarrowCols = 3;      // coverRect: rectangles of at most this many columns (warp-wide) walk them in a loop
+
+// Corner classification of one block (Rasterizer.h:272-303): 0 = skipped ("all out" with the reference's special
+// case), 1 = fully covered (drawBlock<false>: all 64 pixels, no edge tests), 2 = partially covered (drawBlock<true>).
+SWR_HD int classifyBlock(const float4 h0, const float4 h1, const float4 h2, int gx, int gy, BlockEdges &E)
 {
-    const float ea[3] = { h0.x, h0.w, h1.z }, eb[3] = { h0.y, h1.x, h1.w }, ec[3] = { h0.z, h1.y, h2.x };
+    E.ea[0] = h0.x; E.ea[1] = h0.w; E.ea[2] = h1.z;
+    E.eb[0] = h0.y; E.eb[1] = h1.x; E.eb[2] = h1.w;
+    const float ec[3] = { h0.z, h1.y, h2.x };
     const uint32_t flags = f2u(h2.y);
     const float negTiny = u2f(0x80000001u);
-    const float thr[3] = { (flags & kTie0) ? negTiny : 0.0f, (flags & kTie1) ? negTiny : 0.0f, (flags & kTie2) ? negTiny : 0.0f };
+    E.thr[0] = (flags & kTie0) ? negTiny : 0.0f; E.thr[1] = (flags & kTie1) ? negTiny : 0.0f; E.thr[2] = (flags & kTie2) ? negTiny : 0.0f;
     const float xf = fadd(i2f(gx), 0.5f), yf = fadd(i2f(gy), 0.5f);
     const float s = 7.0f;
-    float e00[3], a7[3];
     bool in[4][3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        a7[k] = fmul(ea[k], s);
-        e00[k] = fadd(fadd(fmul(ea[k], xf), fmul(eb[k], yf)), ec[k]);      // EdgeData.h:37-42
-        const float e01 = fadd(e00[k], fmul(eb[k], s));                    // stepY(s)
-        const float e10 = fadd(e00[k], a7[k]);                             // stepX(s)
-        const float e11 = fadd(e01, a7[k]);
-        in[0][k] = e00[k] > thr[k]; in[1][k] = e01 > thr[k];
-        in[2][k] = e10 > thr[k]; in[3][k] = e11 > thr[k];
+        const float a7 = fmul(E.ea[k], s);
+        E.e00[k] = fadd(fadd(fmul(E.ea[k], xf), fmul(E.eb[k], yf)), ec[k]);   // EdgeData.h:37-42
+        const float e01 = fadd(E.e00[k], fmul(E.eb[k], s));                   // stepY(s)
+        const float e10 = fadd(E.e00[k], a7);                                 // stepX(s)
+        const float e11 = fadd(e01, a7);
+        in[0][k] = E.e00[k] > E.thr[k]; in[1][k] = e01 > E.thr[k];
+        in[2][k] = e10 > E.thr[k]; in[3][k] = e11 > E.thr[k];
     }
     int all = 0;
     bool same = true;
@@ -189,47 +202,89 @@ SWR_HD uint64_t coverBlock(const float4 h0, const float4 h1, const float4 h2, in
         all += (in[j][0] && in[j][1] && in[j][2]) ? 1 : 0;
         same = same && ((in[j][0] == in[j][1]) == in[j][2]);               // C++ chained '==' (Rasterizer.h:287-290)
     }
-    if (all == 4) return ~0ull;                                            // drawBlock<false>
-    if (all == 0 && same) return 0ull;                                     // "special case": block skipped
+    if (all == 4) return 1;
+    if (all == 0 && same) return 0;
+    return 2;
+}
 
-    // row by row, exact row maxima from the full 7-add chains
-    uint64_t mask = 0;
-    float r0 = e00[0], r1 = e00[1], r2 = e00[2];
-    const bool up0 = ea[0] > 0, up1 = ea[1] > 0, up2 = ea[2] > 0;
-#pragma unroll 1
-    for (int yy = 0; yy < 8; ++yy) {
-        float l0 = r0, l1 = r1, l2 = r2;
+// Per-pixel tests of a partially covered block inside the pixel rectangle (rx0, ry0)-(rx1, ry1) (the part of the
+// primitive's certified bounds in this block, geometry.cuh: tightPixelBounds), as R rows x C columns starting at
+// (rx0, ry0).  R and C are the same for every lane of a warp (the warp's maxima), so the loops never diverge;
+// rows / columns past a lane's own rectangle are masked off.  (The reference walks all 64 pixels of such a block; the
+// rows it adds nothing in are exactly the ones outside the certified bounds.)  The values are the reference's: the rows above and
+// the columns left of the rectangle still take their adds (the chains are replayed, not re-derived).
+SWR_HD uint64_t coverRect(const BlockEdges &E, int rx0, int ry0, int rx1, int ry1, int R, int C)
+{
+    float r0 = E.e00[0], r1 = E.e00[1], r2 = E.e00[2];
 #pragma unroll
-        for (int xx = 0; xx < 7; ++xx) { l0 = fadd(l0, ea[0]); l1 = fadd(l1, ea[1]); l2 = fadd(l2, ea[2]); }
-        // the row's maximum per edge: last chain value for a > 0, first one otherwise (a NaN coefficient lands
-        // on the first value too, which is then the only one of the row that is not NaN: still exact)
-        const float m0 = up0 ? l0 : r0, m1 = up1 ? l1 : r1, m2 = up2 ? l2 : r2;
-        if (m0 > thr[0] && m1 > thr[1] && m2 > thr[2]) {
-            float v0 = r0, v1 = r1, v2 = r2;
-            uint32_t rowMask = 0;
+    for (int i = 0; i < 7; ++i)
+        if (i < ry0) { r0 = fadd(r0, E.eb[0]); r1 = fadd(r1, E.eb[1]); r2 = fadd(r2, E.eb[2]); }
+    const uint32_t colMask = rx0 <= rx1 ? ((0xffu >> (7 - rx1)) & (0xffu << rx0)) : 0u;
+    uint64_t mask = 0;
+#pragma unroll 1
+    for (int rr = 0; rr < R; ++rr) {
+        float v0 = r0, v1 = r1, v2 = r2;
+        uint32_t rowMask = 0;
+        if (C > kNarrowCols) {
+            // all 8 pixels of the row, unrolled (4 instructions per test, no loop, no lead-in)
 #pragma unroll
             for (int xx = 0; xx < 8; ++xx) {
 #if defined(__CUDA_ARCH__)
-                // the three compares chained into one predicate + a predicated OR: 4 instructions per pixel
-                // (left to itself nvcc materialises every compare with SELs: ~7 per pixel)
+                // the three compares chained into one predicate + a predicated OR (nvcc materialises them with SELs otherwise)
                 asm("{\n\t.reg .pred p;\n\t"
                     "setp.gt.f32 p, %1, %4;\n\t"
                     "setp.gt.and.f32 p, %2, %5, p;\n\t"
                     "setp.gt.and.f32 p, %3, %6, p;\n\t"
                     "@p or.b32 %0, %0, %7;\n\t}"
                     : "+r"(rowMask)
-                    : "f"(v0), "f"(v1), "f"(v2), "f"(thr[0]), "f"(thr[1]), "f"(thr[2]), "r"(1u << xx));
+                    : "f"(v0), "f"(v1), "f"(v2), "f"(E.thr[0]), "f"(E.thr[1]), "f"(E.thr[2]), "r"(1u << xx));
 #else
-                if (v0 > thr[0] && v1 > thr[1] && v2 > thr[2]) rowMask |= 1u << xx;
+                if (v0 > E.thr[0] && v1 > E.thr[1] && v2 > E.thr[2]) rowMask |= 1u << xx;
 #endif
-                v0 = fadd(v0, ea[0]); v1 = fadd(v1, ea[1]); v2 = fadd(v2, ea[2]);
+                if (xx < 7) { v0 = fadd(v0, E.ea[0]); v1 = fadd(v1, E.ea[1]); v2 = fadd(v2, E.ea[2]); }
             }
-            mask |= (uint64_t)rowMask << (yy * 8);
+        } else {
+            // a few columns: lead-in adds up to the rectangle, then C tests
+#pragma unroll
+            for (int i = 0; i < 7; ++i)
+                if (i < rx0) { v0 = fadd(v0, E.ea[0]); v1 = fadd(v1, E.ea[1]); v2 = fadd(v2, E.ea[2]); }
+            uint32_t bit = 1u << rx0;
+#pragma unroll 1
+            for (int cc = 0; cc < C; ++cc) {
+#if defined(__CUDA_ARCH__)
+                asm("{\n\t.reg .pred p;\n\t"
+                    "setp.gt.f32 p, %1, %4;\n\t"
+                    "setp.gt.and.f32 p, %2, %5, p;\n\t"
+                    "setp.gt.and.f32 p, %3, %6, p;\n\t"
+                    "@p or.b32 %0, %0, %7;\n\t}"
+                    : "+r"(rowMask)
+                    : "f"(v0), "f"(v1), "f"(v2), "f"(E.thr[0]), "f"(E.thr[1]), "f"(E.thr[2]), "r"(bit));
+#else
+                if (v0 > E.thr[0] && v1 > E.thr[1] && v2 > E.thr[2]) rowMask |= bit;
+#endif
+                bit <<= 1;
+                v0 = fadd(v0, E.ea[0]); v1 = fadd(v1, E.ea[1]); v2 = fadd(v2, E.ea[2]);
+            }
         }
-        r0 = fadd(r0, eb[0]); r1 = fadd(r1, eb[1]); r2 = fadd(r2, eb[2]);
+        const int yy = ry0 + rr;
+        if (yy <= ry1) mask |= (uint64_t)(rowMask & colMask) << (yy * 8);
+        r0 = fadd(r0, E.eb[0]); r1 = fadd(r1, E.eb[1]); r2 = fadd(r2, E.eb[2]);
     }
-    (void)a7;
     return mask;
+}
+
+// Scalar form (host checks, and the reference for the warp-cooperative use in the tile kernel).
+SWR_HD uint64_t coverBlock(const float4 h0, const float4 h1, const float4 h2, int gx, int gy, int rx0, int ry0, int rx1, int ry1)
+{
+    BlockEdges E;
+    const int cls = classifyBlock(h0, h1, h2, gx, gy, E);
+    if (cls == 1) return ~0ull;                                            // drawBlock<false>
+    if (cls == 0) return 0ull;                                             // "special case": block skipped
+    return coverRect(E, rx0, ry0, rx1, ry1, ry1 - ry0 + 1, rx1 - rx0 + 1);
+}
+SWR_HD uint64_t coverBlock(const float4 h0, const float4 h1, const float4 h2, int gx, int gy)
+{
+    return coverBlock(h0, h1, h2, gx, gy, 0, 0, 7, 7);
 }
 
 // Exact emptiness test of one 8x8 block (Block mode): for every edge the largest of the 64 per-pixel
@@ -601,8 +656,8 @@ __global__ void __launch_bounds__(kTileThreads, SWR_TILE_MINB) tileKernel(const 
         const bool prune = MODE == SWR_DRAW_TRIANGLE && nItems >= 3u * nQ;
         for (uint32_t q = tid; q < nQ; q += kTileThreads) {
             const uint32_t rg = qRange[q];
-            const int bx0 = rg & 0xff, by0 = (rg >> 8) & 0xff, nx = (int)((rg >> 16) & 0xff) - bx0 + 1;
-            const int n = nx * ((int)(rg >> 24) - by0 + 1);
+            const int bx0 = rangeBx0(rg), by0 = rangeBy0(rg), nx = rangeBx1(rg) - bx0 + 1;
+            const int n = nx * (rangeBy1(rg) - by0 + 1);
             uint32_t valid = n >= 32 ? 0xffffffffu : (1u << n) - 1u;
             if (prune && n <= kPruneMax) {
                 const uint32_t rec = qRec[q];
@@ -624,7 +679,7 @@ __global__ void __launch_bounds__(kTileThreads, SWR_TILE_MINB) tileKernel(const 
             auto itemCount = [&](uint32_t q) __attribute__((always_inline)) -> uint32_t {
                 if (q >= nQ) return 0u;
                 const uint32_t rg = qRange[q];
-                const int n = ((int)((rg >> 16) & 0xff) - (int)(rg & 0xff) + 1) * ((int)(rg >> 24) - (int)((rg >> 8) & 0xff) + 1);
+                const int n = (rangeBx1(rg) - rangeBx0(rg) + 1) * (rangeBy1(rg) - rangeBy0(rg) + 1);
                 return n <= kPruneMax ? (uint32_t)__popc(qValid[q]) : (uint32_t)n;
             };
             const uint32_t c0 = itemCount(2 * tid), c1 = itemCount(2 * tid + 1);
@@ -638,8 +693,11 @@ __global__ void __launch_bounds__(kTileThreads, SWR_TILE_MINB) tileKernel(const 
         }
 
         if (timing) { const long long c = clock64(); cycA0 += c - cycMark; cycMark = c; }
-        // A: one thread per (primitive, block) item
-        for (uint32_t it = tid; it < nItems; it += kTileThreads) {
+        // A: one thread per (primitive, block) item.  The loop is warp-uniform (every lane takes part in the warp's
+        // reductions of coverRect's loop bounds; lanes without an item contribute nothing).
+        for (uint32_t itBase = 0; itBase < nItems; itBase += kTileThreads) {
+            const uint32_t it = itBase + tid;
+            const bool ivalid = it < nItems;
             uint32_t lo = 0;                                 // largest q < nQ with qItem[q] <= it (qItem[0] = 0)
 #pragma unroll
             for (uint32_t step = kQueue / 2; step > 0; step >>= 1) {
@@ -647,36 +705,53 @@ __global__ void __launch_bounds__(kTileThreads, SWR_TILE_MINB) tileKernel(const 
                 if (mid < nQ && qItem[mid] <= it) lo = mid;
             }
             const uint32_t q = lo, rec = qRec[q], rg = qRange[q];
-            const int bx0 = rg & 0xff, by0 = (rg >> 8) & 0xff, nx = (int)((rg >> 16) & 0xff) - bx0 + 1;
-            const int nAll = nx * ((int)(rg >> 24) - by0 + 1);
-            const int k = (int)(it - qItem[q]);
+            const int bx0 = rangeBx0(rg), by0 = rangeBy0(rg), nx = rangeBx1(rg) - bx0 + 1;
+            const int nAll = nx * (rangeBy1(rg) - by0 + 1);
+            const int k = ivalid ? (int)(it - qItem[q]) : 0;
             const int li = nAll <= kPruneMax ? nthSetBit32(qValid[q], k) : k;     // k-th surviving item -> block
             const int liy = divSmall(li, nx);
             const int bx = bx0 + li - liy * nx, by = by0 + liy;
             const int gx = X0 + bx * 8, gy = Y0 + by * 8;
-            uint64_t m;
+            uint64_t m = 0;
             if (MODE == SWR_DRAW_TRIANGLE) {
                 const float4 h2 = t.head[(size_t)rec * 3 + 2];
-                if (f2u(h2.y) & kModeSpan) {
+                const bool spanMode = (f2u(h2.y) & kModeSpan) != 0;
+                // the primitive's pixel bounds, clipped to this block
+                const int rx0 = max((int)(rg & 63u) - bx * 8, 0), ry0 = max((int)((rg >> 6) & 63u) - by * 8, 0);
+                const int rx1 = min((int)((rg >> 12) & 63u) - bx * 8, 7), ry1 = min((int)((rg >> 18) & 63u) - by * 8, 7);
+                BlockEdges E;
+                int cls = 0;
+                if (ivalid && !spanMode) cls = classifyBlock(t.head[(size_t)rec * 3], t.head[(size_t)rec * 3 + 1], h2, gx, gy, E);
+                else {
+#pragma unroll
+                    for (int e = 0; e < 3; ++e) { E.ea[e] = 0.0f; E.eb[e] = 0.0f; E.thr[e] = 0.0f; E.e00[e] = 0.0f; }
+                }
+                if (cls == 1) m = ~0ull;
+                const bool partial = cls == 2;
+                const int R = __reduce_max_sync(0xffffffffu, partial ? ry1 - ry0 + 1 : 0);
+                const int Cw = __reduce_max_sync(0xffffffffu, partial ? rx1 - rx0 + 1 : 0);
+                if (R > 0) {
+                    const uint64_t pm = coverRect(E, partial ? rx0 : 0, partial ? ry0 : 0, partial ? rx1 : -1, partial ? ry1 : -1, R, Cw);
+                    if (partial) m = pm;
+                }
+                if (ivalid && spanMode) {
                     const float4 *sp = t.span + (size_t)rec * 3;
                     m = coverSpan(sp[0], sp[1], sp[2], gx, gy, t.scMinX, t.scMaxX);
-                } else {
-                    m = coverBlock(t.head[(size_t)rec * 3], t.head[(size_t)rec * 3 + 1], h2, gx, gy);
                 }
             } else if (MODE == SWR_DRAW_LINE) {
-                m = coverLine(t.head[(size_t)rec * 3], t.head[(size_t)rec * 3 + 1], gx, gy, t);
-            } else {
+                if (ivalid) m = coverLine(t.head[(size_t)rec * 3], t.head[(size_t)rec * 3 + 1], gx, gy, t);
+            } else if (ivalid) {
                 const float4 h0 = t.head[(size_t)rec * 3];
                 const int lx = f2i(h0.x) - gx, ly = f2i(h0.y) - gy;
                 m = ((unsigned)lx < 8u && (unsigned)ly < 8u) ? 1ull << (ly * 8 + lx) : 0ull;
             }
-            sMasks[it] = m;
-            if ((SWR_PREFETCH & 2) && m) {
+            if (ivalid) sMasks[it] = m;
+            if ((SWR_PREFETCH & 2) && ivalid && m) {
                 const char *pp = (const char *)(t.params + (size_t)rec * t.paramStride);
                 prefetchL2(pp);
                 prefetchL2(pp + t.paramStride * 4 - 4);
             }
-            if (m) atomicOr(&sBlockmap[(by * BPR + bx) * QW + (q >> 5)], 1u << (q & 31));
+            if (ivalid && m) atomicOr(&sBlockmap[(by * BPR + bx) * QW + (q >> 5)], 1u << (q & 31));
         }
         __syncthreads();
 
@@ -725,8 +800,8 @@ __global__ void __launch_bounds__(kTileThreads, SWR_TILE_MINB) tileKernel(const 
                     q = (uint32_t)(wc + wl) * 32u + (uint32_t)nthSetBit32(wbm, (int)(j - wbase));
                     rec = qRec[q];
                     const uint32_t rg = qRange[q];
-                    const int bx0 = rg & 0xff, by0 = (rg >> 8) & 0xff, nx = (int)((rg >> 16) & 0xff) - bx0 + 1;
-                    const int nAll = nx * ((int)(rg >> 24) - by0 + 1);
+                    const int bx0 = rangeBx0(rg), by0 = rangeBy0(rg), nx = rangeBx1(rg) - bx0 + 1;
+                    const int nAll = nx * (rangeBy1(rg) - by0 + 1);
                     const int li = (by - by0) * nx + (bx - bx0);
                     const int k = nAll <= kPruneMax ? __popc(qValid[q] & ((1u << li) - 1u)) : li;
                     m = sMasks[qItem[q] + (uint32_t)k];
@@ -854,10 +929,10 @@ __global__ void __launch_bounds__(kTileThreads, SWR_TILE_MINB) tileKernel(const 
                         bb.x0 = (int16_t)(w[2 * k] & 0xffffu); bb.y0 = (int16_t)(w[2 * k] >> 16);
                         bb.x1 = (int16_t)(w[2 * k + 1] & 0xffffu); bb.y1 = (int16_t)(w[2 * k + 1] >> 16);
                         if (((pend >> k) & 1u) && boxOverlaps(bb, X0, Y0, X1, Y1)) {
-                            const int bx0 = (max((int)bb.x0, X0) - X0) >> 3, by0 = (max((int)bb.y0, Y0) - Y0) >> 3;
-                            const int bx1 = (min((int)bb.x1, X1) - X0) >> 3, by1 = (min((int)bb.y1, Y1) - Y0) >> 3;
-                            range[k] = (uint32_t)bx0 | ((uint32_t)by0 << 8) | ((uint32_t)bx1 << 16) | ((uint32_t)by1 << 24);
-                            items[k] = (uint32_t)((bx1 - bx0 + 1) * (by1 - by0 + 1));
+                            const int lx0 = max((int)bb.x0, X0) - X0, ly0 = max((int)bb.y0, Y0) - Y0;
+                            const int lx1 = min((int)bb.x1, X1) - X0, ly1 = min((int)bb.y1, Y1) - Y0;
+                            range[k] = packRange(lx0, ly0, lx1, ly1);
+                            items[k] = (uint32_t)(((lx1 >> 3) - (lx0 >> 3) + 1) * ((ly1 >> 3) - (ly0 >> 3) + 1));
                             ++cnt;
                             sum += items[k];
                         } else {

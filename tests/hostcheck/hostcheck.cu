@@ -169,6 +169,7 @@ int run(swr_scene *s)
     g.paramStride = paramFloats(s->draw_mode, g.nA, g.nP, g.useZ, g.useW);
     uint32_t errorFlags[2] = { 0, 0 };
     g.errorFlag = errorFlags;
+    g.noTightBox = getenv("HOSTCHECK_NO_TIGHT_BOX") ? 1 : 0;
 
     const size_t cap = (size_t)nprim * (s->draw_mode == 2 ? kMaxFan : 1) + 1;
     Store st;
@@ -247,7 +248,9 @@ int run(swr_scene *s)
                 if (s->draw_mode == 2) {
                     if (f2u(h2.y) & kModeSpan) m = coverSpan(t.span[(size_t)rec * 3], t.span[(size_t)rec * 3 + 1], t.span[(size_t)rec * 3 + 2], gx, gy, t.scMinX, t.scMaxX);
                     else {
-                        m = coverBlock(h0, h1, h2, gx, gy);
+                        // as the tile kernel calls it: only the part of the certified pixel bounds inside this block
+                        m = coverBlock(h0, h1, h2, gx, gy, std::max((int)bb.x0 - gx, 0), std::max((int)bb.y0 - gy, 0),
+                                       std::min((int)bb.x1 - gx, 7), std::min((int)bb.y1 - gy, 7));
                         if (!blockMayBeCovered(h0, h1, h2, gx, gy)) { statPruned++; if (m != 0) pruneViolations++; }
                     }
                 } else if (s->draw_mode == 1) {
@@ -315,6 +318,87 @@ extern "C" int hostcheck_draw(swr_scene *s)
     }
     default: return -2;
     }
+}
+
+
+// ---- certified pixel bounds (geometry.cuh: tightPixelBounds) against the reference's full block walk ----------
+// For `n` pseudo-random screen-space triangles of class `kind` the record is set up twice, with the certified
+// bounds and with the reference's 8-aligned block box; the coverage of every block of the reference box is
+// evaluated in full (coverBlock over the whole block) and (a) every covered pixel must lie inside the certified
+// bounds, (b) the rectangle-limited coverBlock must return exactly the full mask.  Returns the number of
+// violations; *checked = triangles that reached the rasterizer, *tightened = pixels excluded by the bounds.
+namespace {
+uint64_t rngState = 0;
+double rnd01()
+{
+    rngState = rngState * 6364136223846793005ull + 1442695040888963407ull;
+    return (double)((rngState >> 11) & ((1ull << 53) - 1)) / (double)(1ull << 53);
+}
+}
+extern "C" long hostcheck_tight_box_fuzz(int kind, long n, unsigned long long seed, int width, int height, long *checked, long *tightened)
+{
+    typedef CVert<3, 0> V;
+    rngState = seed * 2654435761ull + 12345u;
+    GeomArgs g;
+    memset(&g, 0, sizeof(g));
+    g.drawMode = SWR_DRAW_TRIANGLE;
+    g.cullMode = SWR_CULL_NONE; g.rasterMode = SWR_RASTER_BLOCK;
+    g.scMinX = 0; g.scMinY = 0; g.scMaxX = width; g.scMaxY = height;
+    g.nA = 0; g.nP = 0; g.useZ = 0; g.useW = 0;
+    g.paramStride = 4;
+    uint32_t errorFlags[2] = { 0, 0 };
+    g.errorFlag = errorFlags;
+    std::vector<float4> head(6);
+    std::vector<float> params(16);
+    std::vector<float4> span(6);
+    g.head = head.data(); g.params = params.data(); g.span = span.data();
+    long bad = 0;
+    *checked = 0; *tightened = 0;
+    for (long it = 0; it < n; ++it) {
+        V v[3];
+        memset(v, 0, sizeof(v));
+        const double cx = rnd01() * width, cy = rnd01() * height;
+        for (int k = 0; k < 3; ++k) {
+            double x, y;
+            switch (kind) {
+            case 0: x = cx + (rnd01() - 0.5) * 3.0; y = cy + (rnd01() - 0.5) * 3.0; break;                     // tiny
+            case 1: x = rnd01() * width; y = rnd01() * height; break;                                             // screen sized
+            case 2: x = cx + (rnd01() - 0.5) * 40.0; y = cy + (rnd01() - 0.5) * 40.0; break;                      // a few blocks
+            case 3: x = cx + (k == 2 ? 1e-3 * (rnd01() - 0.5) : 0.0) + (k == 1 ? 3000.0 * (rnd01() - 0.5) : 0.0); // slivers
+                    y = cy + (k == 1 ? 3000.0 * (rnd01() - 0.5) : 0.0) * 0.37 + (k == 2 ? 2.0 * (rnd01() - 0.5) : 0.0); break;
+            case 4: x = (double)(int)(cx + (rnd01() - 0.5) * 12.0) + 0.5; y = (double)(int)(cy + (rnd01() - 0.5) * 12.0) + 0.5; break;   // vertices on pixel centres
+            case 5: x = (double)(int)(cx + (rnd01() - 0.5) * 20.0); y = (double)(int)(cy + (rnd01() - 0.5) * 20.0); break;             // vertices on pixel corners
+            case 6: x = cx + (rnd01() - 0.5) * 0.05; y = cy + (rnd01() - 0.5) * 0.05; break;                      // far below a pixel
+            default: x = (rnd01() - 0.25) * 2.0 * width; y = (rnd01() - 0.25) * 2.0 * height; break;              // partly off screen (guard band)
+            }
+            v[k].x = (float)x; v[k].y = (float)y; v[k].z = 0.5f; v[k].w = 1.0f;
+        }
+        g.noTightBox = 0;
+        const Box16 tight = emitScreenTriangle<3, 0>(g, 0, 0, true, v[0], v[1], v[2]);
+        g.noTightBox = 1;
+        const Box16 ref = emitScreenTriangle<3, 0>(g, 1, 0, true, v[0], v[1], v[2]);
+        if (ref.x0 > ref.x1) { if (tight.x0 <= tight.x1) ++bad; continue; }
+        ++*checked;
+        const float4 h0 = head[3], h1 = head[4], h2 = head[5];
+        if (tight.x0 <= tight.x1 && (memcmp(&head[0], &head[3], 48) != 0)) ++bad;      // same record either way
+        for (int gy = ref.y0 & ~7; gy <= ref.y1; gy += 8)
+            for (int gx = ref.x0 & ~7; gx <= ref.x1; gx += 8) {
+                const uint64_t full = coverBlock(h0, h1, h2, gx, gy);
+                uint64_t lim = 0;
+                const bool touches = tight.x0 <= tight.x1 && tight.x0 <= gx + 7 && tight.x1 >= gx && tight.y0 <= gy + 7 && tight.y1 >= gy;
+                if (touches)
+                    lim = coverBlock(h0, h1, h2, gx, gy, std::max((int)tight.x0 - gx, 0), std::max((int)tight.y0 - gy, 0),
+                                     std::min((int)tight.x1 - gx, 7), std::min((int)tight.y1 - gy, 7));
+                if (lim != full) ++bad;
+                for (int bit = 0; bit < 64; ++bit) {
+                    const int x = gx + (bit & 7), y = gy + (bit >> 3);
+                    const bool inTight = tight.x0 <= tight.x1 && x >= tight.x0 && x <= tight.x1 && y >= tight.y0 && y <= tight.y1;
+                    if (((full >> bit) & 1) && !inTight) ++bad;
+                    if (!inTight) ++*tightened;
+                }
+            }
+    }
+    return bad;
 }
 
 extern "C" int hostcheck_draw_raster_triangles(swr_scene *, const float *, int64_t) { return -1; }

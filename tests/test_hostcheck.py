@@ -47,3 +47,33 @@ def test_device_math_on_host_matches_oracle(oracle, hostcheck, label, scene):
     got, want = hostcheck(scene), oracle.run(scene, "oracle")
     assert got["fragments"] == want["fragments"]
     assert not common.diff_buffers(got, want), label
+
+
+FUZZ = [  # (class of triangles, how many, surface)
+    (0, 150000, 3840, 2160), (2, 100000, 3840, 2160), (4, 100000, 3840, 2160), (5, 100000, 3840, 2160), (6, 100000, 3840, 2160),
+    (1, 300, 3840, 2160), (3, 5000, 3840, 2160), (7, 300, 3840, 2160),
+    (0, 100000, 16384, 16384), (2, 50000, 16384, 16384), (3, 3000, 16384, 16384), (4, 50000, 16384, 16384), (6, 50000, 16384, 16384),
+]
+
+
+@pytest.mark.parametrize("kind,n,w,h", FUZZ, ids=[f"kind{k}_{w}" for k, _, w, _ in FUZZ])
+def test_certified_pixel_bounds_never_drop_a_fragment(hostcheck, kind, n, w, h):
+    """geometry.cuh tightPixelBounds: over random tiny / block-sized / screen-sized / sliver / pixel-centre /
+    pixel-corner / sub-pixel / guard-band triangles, no pixel the reference's full block walk covers lies outside the
+    certified bounds, and the rectangle-limited coverage equals the full one (0 violations)."""
+    lib = C.CDLL(SO)
+    f = lib.hostcheck_tight_box_fuzz
+    f.argtypes = [C.c_int, C.c_long, C.c_ulonglong, C.c_int, C.c_int, C.POINTER(C.c_long), C.POINTER(C.c_long)]
+    f.restype = C.c_long
+    checked, excluded = C.c_long(), C.c_long()
+    bad = f(kind, n, 1000 + kind, w, h, C.byref(checked), C.byref(excluded))
+    assert bad == 0
+    assert checked.value > n // 2 and excluded.value > 0
+
+
+def test_device_math_without_the_certified_bounds(oracle, hostcheck, monkeypatch):
+    """The same records with the reference's 8-aligned block boxes (GeomArgs::noTightBox) give the same pixels."""
+    monkeypatch.setenv("HOSTCHECK_NO_TIGHT_BOX", "1")
+    for label, scene in SCENES[::9]:
+        got, want = hostcheck(scene), oracle.run(scene, "oracle")
+        assert got["fragments"] == want["fragments"] and not common.diff_buffers(got, want), label

@@ -22,6 +22,11 @@ constexpr int kBinWarps = kBinThreads / 32;
 constexpr int kBinChunkList = 1024;
 constexpr uint32_t kBinOverflow = 0xffffffffu;
 
+// group list entry: group id (27 bits) | records of the group - 1 (5 bits); only groups with records are listed
+SWR_HD uint32_t packGroup(uint32_t group, uint32_t count) { return group | ((count - 1u) << 27); }
+SWR_HD uint32_t groupOf(uint32_t entry) { return entry & 0x07ffffffu; }
+SWR_HD uint32_t groupCount(uint32_t entry) { return (entry >> 27) + 1u; }
+
 // exclusive block scan of a packed (hi: count, lo: sum) pair, one barrier, double-buffered scratch
 SWR_D uint64_t binScan(uint64_t v, uint64_t &total, uint64_t *scratch, int &phase)
 {
@@ -139,7 +144,7 @@ __global__ void __launch_bounds__(kBinThreads) binKernel(const TileArgs t)
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                     if ((hits >> k) & 1u) {
-                        if (e2 < cap) out[e2] = grp[k];
+                        if (e2 < cap) out[e2] = packGroup(grp[k], t.gcnt[grp[k]]);
                         ++e2;
                     }
                 nOut += (uint32_t)tot2;

@@ -4,17 +4,25 @@
 // HBM layout of one pass (up to `maxPrims` input primitives, R = record index):
 //   bbox   [R]  4 x int16  inclusive pixel bounds of the primitive's fragment footprint
 //                         (min > max  <=>  dead: clipped away, culled, zero area, off-screen)
-//   gbox   [R/32] 4 x int16 union of the 32 records of one group (one warp of the geometry kernel)
+//   gbox   [R/32] 4 x int16 union of the records of one group (one warp of the geometry kernel)
 //   head   [R]  3 x float4 edge equations / line start+step / point position, flags, ordinal
 //   params [R]  paramStride floats: interpolation planes, one float4 (a,b,c,0) each, in the order z?, invw?, avar[], pvar[]
 //               (lines: (start, step) pairs; points: values)
 //   span   [R]  3 x float4 (Span / Adaptive only) the two scan-converted halves
 //   tilemap[tile][chunk/32] one bit per (screen tile, chunk): chunk may touch the tile
-// Records [0, maxPrims) are the "original slots" (record = primitive index within the pass, so
-// record order is submission order); clipper fan extras of batch b live in a bump-allocated,
-// 32-aligned range extra[b] = {base, count} behind them.  Chunk 2b = original slots of batch b,
+//   gcnt   [R/32] records of the group (they sit at the front of its 32 slots)
+// Records [0, maxPrims) are the "original slots": group G (32 consecutive primitives of the pass, one warp of the
+// geometry kernel) owns the slots [32 G, 32 G + 32) and fills the first gcnt[G] of them with its surviving primitives
+// IN SUBMISSION ORDER (culled / clipped-away / off-screen primitives and, with several ranks, primitives that touch
+// no tile of the rank leave no record; the slots behind the count are neither written nor read).  Clipper fan extras
+// of batch b live in a bump-allocated, 32-aligned range extra[b] = {base, count} behind the original slots.  Chunk 2b = original slots of batch b,
 // chunk 2b+1 = its extras: ascending chunk id, then ascending record, is exactly the reference's
 // emission order (VertexProcessor.cpp:252-261, Rasterizer.h:134-141).
+//
+// Several ranks (sort-first, one GPU each): every rank owns the screen tiles t with (tx + 3 ty) % world == rank and
+// keeps its own copy of the arrays above, holding only the records that touch its tiles.  The geometry stage is
+// sharded by batches: the rank that runs batch b writes each surviving record straight into the scratch of the
+// owners of the tiles it touches -- its own or, through peer mappings over NVLink, another GPU's (RecordSink).
 #pragma once
 
 #include <stdint.h>
@@ -84,6 +92,22 @@ enum : uint32_t {
 
 struct RenderTargetDesc { void *ptr; int32_t pitch; int32_t pad; };
 
+constexpr int kMaxRanks = SWR_MAX_RANKS;
+constexpr int kShardBatches = 16;    // sharded geometry: runs of this many batches go to the ranks round-robin
+
+// One rank's per-pass scratch as a geometry kernel sees it: its own, or a peer's mapped over NVLink.
+struct RecordSink {
+    Box16 *bbox;
+    Box16 *gbox;
+    float4 *head;
+    float *params;
+    float4 *span;
+    uint32_t *tilemap;
+    uint8_t *gcnt;                   // per group: records at the front of its 32 slots
+    uint2 *extra;                    // per batch {base, count} of the fan extras
+    uint32_t *errorFlag;             // [0]: per draw (bit 0 voids the draw on that rank), [1]: sticky copy
+};
+
 // Arguments of the geometry kernel (one launch = one pass).
 struct GeomArgs {
     // input
@@ -103,24 +127,24 @@ struct GeomArgs {
     int32_t scMinX, scMinY, scMaxX, scMaxY;   // Rasterizer.h:81-87 (max exclusive)
     // what the pixel shader interpolates (TriangleEquations uses the PIXEL shader's counts)
     int32_t nA, nP, useZ, useW;
-    // output
-    Box16 *bbox;
-    Box16 *gbox;
-    float4 *head;
-    float *params;
-    float4 *span;
+    // output: sink[r] = scratch of rank r.  Replicated geometry (shard == 0): only sink[rank] is set and records
+    // for other ranks are dropped; sharded geometry: all `world` sinks are set.
+    RecordSink sink[kMaxRanks];
     int32_t paramStride;
-    uint32_t *tilemap;
     int32_t chunkWords;              // 32-bit words per tilemap row
     int32_t tileShift;               // log2(tile size in pixels)
     int32_t tilesX, tilesY;
-    uint2 *extra;                    // per batch {base, count}
-    uint32_t *extraAlloc;            // bump allocator cursor (record index), starts at extrasBegin
-    uint32_t extrasEnd;              // capacity end (record index)
-    uint32_t *errorFlag;
-    float *dbgVerts;                 // optional: 12 floats per record (3 x xyzw, screen space)
-    int32_t rank, world;             // sort-first: records that touch no tile owned by this rank are dropped
+    uint32_t *extraAlloc;            // bump allocator cursor of this rank's share of the extras range (record index)
+    uint32_t extrasEnd;              // ... and its end
+    int32_t rank, world;             // sort-first tile ownership
+    int32_t shard;                   // 1: this launch runs only the batches of `rank` (kShardBatches-cyclic) and pushes to the owners
     int32_t noTightBox;              // debug: keep the reference's 8-aligned block box instead of the certified pixel bounds
+    // optional stream-out (VertexProcessor with a foreign IRasterizer): per input primitive 3 RasterizerVertex-sized
+    // records + 3 indices in the reference's batch layout; see geometry.cuh streamOutKernel
+    void *soVerts;
+    int32_t *soIndices;
+    uint32_t *soCounts;
+    uint32_t soExtraCap;
 };
 
 // Arguments of the tile kernel.
@@ -136,6 +160,7 @@ struct TileArgs {
     int32_t numChunks;               // 2 * batches in the pass
     int32_t numPrims;
     const uint2 *extra;
+    const uint8_t *gcnt;             // per group: records at the front of its 32 slots (geometry.cuh)
     int32_t tilesX, tilesY;
     int32_t rank, world;             // sort-first ownership: (tx + 3*ty) % world == rank
     int32_t rtWidth, rtHeight;
@@ -170,20 +195,30 @@ SWR_HD int paramFloats(int drawMode, int nA, int nP, int useZ, int useW)
 
 SWR_HD bool tileOwned(int tx, int ty, int rank, int world) { return world <= 1 || ((tx + 3 * ty) % world) == rank; }
 
-// Does the pixel box touch a tile owned by `rank`?  (owner = (tx + 3 ty) mod world: any `world`
-// consecutive tiles of a row contain every owner, so only narrow boxes need the loop.)
-SWR_HD bool boxTouchesOwnedTile(const Box16 b, int tileShift, int tilesX, int tilesY, int rank, int world)
+// Owners of the tiles a pixel box touches, as a bit mask over the ranks (owner = (tx + 3 ty) mod world: any `world`
+// consecutive tiles of a row contain every owner, so only narrow boxes need the loop).
+SWR_HD uint32_t boxOwnerMask(const Box16 b, int tileShift, int tilesX, int tilesY, int world)
 {
-    if (world <= 1) return true;
+    if (b.x0 > b.x1) return 0u;
     int tx0 = b.x0 >> tileShift, ty0 = b.y0 >> tileShift, tx1 = b.x1 >> tileShift, ty1 = b.y1 >> tileShift;
     if (tx1 > tilesX - 1) tx1 = tilesX - 1;
     if (ty1 > tilesY - 1) ty1 = tilesY - 1;
-    if (tx0 > tx1 || ty0 > ty1) return false;
-    if (tx1 - tx0 + 1 >= world) return true;
-    for (int ty = ty0; ty <= ty1; ++ty)
-        for (int tx = tx0; tx <= tx1; ++tx)
-            if (tileOwned(tx, ty, rank, world)) return true;
-    return false;
+    if (tx0 > tx1 || ty0 > ty1) return 0u;
+    if (world <= 1) return 1u;
+    const uint32_t all = (1u << world) - 1u;
+    if (tx1 - tx0 + 1 >= world) return all;
+    uint32_t m = 0;
+    int o0 = (tx0 + 3 * ty0) % world;
+    for (int ty = ty0; ty <= ty1 && m != all; ++ty) {
+        int o = o0;
+        for (int tx = tx0; tx <= tx1; ++tx) {
+            m |= 1u << o;
+            if (++o == world) o = 0;
+        }
+        o0 += 3;
+        while (o0 >= world) o0 -= world;
+    }
+    return m;
 }
 
 } // namespace detail

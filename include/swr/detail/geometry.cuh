@@ -103,9 +103,10 @@ SWR_HD int clipPolyPlane(const CVert<NA, NP> *in, int n, CVert<NA, NP> *out, int
 }
 
 // Clip a triangle against the planes flagged in `mask`.  bufA holds the 3 input vertices; the
-// result is in *res (bufA or bufB).  Returns the polygon size (0 when fully clipped / overflow).
+// result is in *res (bufA or bufB).  Returns the polygon size (0 when fully clipped, or on overflow of
+// kMaxPoly vertices, which *overflow then reports).
 template <int NA, int NP>
-SWR_HD int clipTriangle(CVert<NA, NP> *bufA, CVert<NA, NP> *bufB, int mask, CVert<NA, NP> **res)
+SWR_HD int clipTriangle(CVert<NA, NP> *bufA, CVert<NA, NP> *bufB, int mask, CVert<NA, NP> **res, bool *overflow = nullptr)
 {
     CVert<NA, NP> *in = bufA, *out = bufB;
     int n = 3;
@@ -113,7 +114,7 @@ SWR_HD int clipTriangle(CVert<NA, NP> *bufA, CVert<NA, NP> *bufB, int mask, CVer
         if (!(mask & (1 << pl))) continue;
         if (n < 3) break;                                   // PolyClipper.cpp:47-48
         n = clipPolyPlane(in, n, out, pl);
-        if (n < 0) { n = 0; break; }
+        if (n < 0) { n = 0; if (overflow) *overflow = true; break; }   // > kMaxPoly vertices: dropped and reported (swr_finish)
         CVert<NA, NP> *t = in; in = out; out = t;
     }
     *res = in;
@@ -316,20 +317,29 @@ SWR_HD bool tightPixelBounds(const EdgeEquation &e0, const EdgeEquation &e1, con
     return true;
 }
 
-// Screen-space triangle -> record `rec`.  Cull / re-orient (VertexProcessor.cpp:319-345), setup
-// (TriangleEquations.h:47-71), footprint (Rasterizer.h:234-255 or the span halves).  Returns the
-// footprint box (dead when the triangle is dropped anywhere on the way).
+// ---- records ---------------------------------------------------------------------------------------
+// A primitive is set up in registers first (its footprint decides whether, and to which ranks, a record is
+// written at all) and stored once its position in the destination's compacted record range is known.
+
+constexpr int kMaxPlanes = 2;        // z, 1/w in front of the avar / pvar planes
+
+// TriangleEquations (TriangleEquations.h:47-71) of one screen-space triangle plus its footprint.
 template <int NA, int NP>
-SWR_HD Box16 emitScreenTriangle(const GeomArgs &g, uint32_t rec, uint32_t ordinal, bool doCull,
-                                const CVert<NA, NP> &s0, const CVert<NA, NP> &s1, const CVert<NA, NP> &s2)
+struct TriRecord {
+    float4 h0, h1, h2;                               // edges, flags, ordinal, area2 (layout of `head`)
+    float pa[kMaxPlanes + NA + NP], pb[kMaxPlanes + NA + NP], pc[kMaxPlanes + NA + NP];   // planes: [0] z, [1] 1/w, avar, pvar
+    SpanHalf bot, top;                               // Span / Adaptive only
+    bool span;
+};
+
+// Screen-space triangle: cull / re-orient (VertexProcessor.cpp:319-345), setup (TriangleEquations.h:47-71),
+// footprint (the certified pixel bounds of the reference's block walk, Rasterizer.h:234-255, or the span halves).
+// Returns the footprint box (dead when the triangle is dropped anywhere on the way).
+template <int NA, int NP, bool SPAN = true>
+SWR_HD Box16 setupScreenTriangle(const GeomArgs &g, uint32_t ordinal, bool doCull,
+                                 const CVert<NA, NP> &s0, const CVert<NA, NP> &s1, const CVert<NA, NP> &s2, TriRecord<NA, NP> &R)
 {
     const CVert<NA, NP> *v0 = &s0, *v1 = &s1, *v2 = &s2;
-    if (g.dbgVerts) {
-        float *d = g.dbgVerts + (size_t)rec * 12;
-        d[0] = s0.x; d[1] = s0.y; d[2] = s0.z; d[3] = s0.w;
-        d[4] = s1.x; d[5] = s1.y; d[6] = s1.z; d[7] = s1.w;
-        d[8] = s2.x; d[9] = s2.y; d[10] = s2.z; d[11] = s2.w;
-    }
     if (doCull) {
         const float facing = fsub(fmul(fsub(s0.x, s1.x), fsub(s2.y, s1.y)), fmul(fsub(s2.x, s1.x), fsub(s0.y, s1.y)));
         if (facing < 0) {
@@ -347,24 +357,20 @@ SWR_HD Box16 emitScreenTriangle(const GeomArgs &g, uint32_t rec, uint32_t ordina
     if (area2 <= 0) return deadBox();                       // Rasterizer.h:231,315
 
     // raster mode of this triangle (Rasterizer.h:413-445; Adaptive's literals are doubles)
-    bool span = g.rasterMode == SWR_RASTER_SPAN;
+    bool span = SPAN && g.rasterMode == SWR_RASTER_SPAN;     // (SPAN == false: the caller knows the mode is Block)
     const float fminX = min3f(v0->x, v1->x, v2->x), fmaxX = max3f(v0->x, v1->x, v2->x);
     const float fminY = min3f(v0->y, v1->y, v2->y), fmaxY = max3f(v0->y, v1->y, v2->y);
-    if (g.rasterMode == SWR_RASTER_ADAPTIVE) {
+    if (SPAN && g.rasterMode == SWR_RASTER_ADAPTIVE) {
         const float orient = fdiv(fsub(fmaxX, fminX), fsub(fmaxY, fminY));
         span = !((double)orient > 0.4 && (double)orient < 1.6);
     }
 
     Box16 box;
+    R.span = span;
     if (span) {
-        SpanHalf bot, top;
-        spanSetup(v0->x, v0->y, v1->x, v1->y, v2->x, v2->y, bot, top);
-        box = spanBox(bot, top, g.scMinX, g.scMaxX);
+        spanSetup(v0->x, v0->y, v1->x, v1->y, v2->x, v2->y, R.bot, R.top);
+        box = spanBox(R.bot, R.top, g.scMinX, g.scMaxX);
         if (box.x0 > box.x1) return box;
-        float4 *sp = g.span + (size_t)rec * 3;
-        sp[0] = mkf4(bot.vx, bot.vy, bot.inv1, bot.inv2);
-        sp[1] = mkf4(top.vx, top.vy, top.inv1, top.inv2);
-        sp[2] = mkf4(u2f((uint32_t)bot.y0), u2f((uint32_t)bot.y1), u2f((uint32_t)top.y0), u2f((uint32_t)top.y1));
     } else {
         int minX = f2i(fminX), maxX = f2i(fmaxX), minY = f2i(fminY), maxY = f2i(fmaxY);
         minX = imax(minX, g.scMinX); maxX = imin(maxX, g.scMaxX);      // max stays the exclusive edge (P11)
@@ -380,55 +386,93 @@ SWR_HD Box16 emitScreenTriangle(const GeomArgs &g, uint32_t rec, uint32_t ordina
         if (box.x0 > box.x1) return box;
     }
 
-    // sort-first: another rank rasterizes every tile this triangle touches -> no record here
-    if (!boxTouchesOwnedTile(box, g.tileShift, g.tilesX, g.tilesY, g.rank, g.world)) return deadBox();
+    const uint32_t flags = (e0.tie ? kTie0 : 0u) | (e1.tie ? kTie1 : 0u) | (e2.tie ? kTie2 : 0u) | (span ? kModeSpan : 0u);
+    R.h0 = mkf4(e0.a, e0.b, e0.c, e1.a);
+    R.h1 = mkf4(e1.b, e1.c, e2.a, e2.b);
+    R.h2 = mkf4(e2.c, u2f(flags), u2f(ordinal), area2);
 
-    uint32_t flags = (e0.tie ? kTie0 : 0u) | (e1.tie ? kTie1 : 0u) | (e2.tie ? kTie2 : 0u) | (span ? kModeSpan : 0u);
-    float4 *hd = g.head + (size_t)rec * 3;
-    hd[0] = mkf4(e0.a, e0.b, e0.c, e1.a);
-    hd[1] = mkf4(e1.b, e1.c, e2.a, e2.b);
-    hd[2] = mkf4(e2.c, u2f(flags), u2f(ordinal), area2);
-
-    // interpolation planes (TriangleEquations.h:59-70), order: z?, invw?, avar[nA], pvar[nP]; one float4 each
-    float4 *pp4 = reinterpret_cast<float4 *>(g.params + (size_t)rec * g.paramStride);
+    // interpolation planes (TriangleEquations.h:59-70)
     const float factor = frcp(area2);
     ParameterEquation pe;
     if (g.useZ) {
         pe.init(v0->z, v1->z, v2->z, e0, e1, e2, factor);
-        *pp4++ = mkf4(pe.a, pe.b, pe.c, 0.0f);
+        R.pa[0] = pe.a; R.pb[0] = pe.b; R.pc[0] = pe.c;
     }
     float iw0 = 0.0f, iw1 = 0.0f, iw2 = 0.0f;
     if (g.useW || g.nP > 0) {
         iw0 = frcp(v0->w); iw1 = frcp(v1->w); iw2 = frcp(v2->w);
         pe.init(iw0, iw1, iw2, e0, e1, e2, factor);
-        *pp4++ = mkf4(pe.a, pe.b, pe.c, 0.0f);
+        R.pa[1] = pe.a; R.pb[1] = pe.b; R.pc[1] = pe.c;
     }
 #pragma unroll
     for (int i = 0; i < NA; ++i) {
         if (i < g.nA) {
             pe.init(v0->a[i], v1->a[i], v2->a[i], e0, e1, e2, factor);
-            *pp4++ = mkf4(pe.a, pe.b, pe.c, 0.0f);
+            R.pa[kMaxPlanes + i] = pe.a; R.pb[kMaxPlanes + i] = pe.b; R.pc[kMaxPlanes + i] = pe.c;
         }
     }
 #pragma unroll
     for (int i = 0; i < NP; ++i) {
         if (i < g.nP) {
             pe.init(fmul(v0->p[i], iw0), fmul(v1->p[i], iw1), fmul(v2->p[i], iw2), e0, e1, e2, factor);
-            *pp4++ = mkf4(pe.a, pe.b, pe.c, 0.0f);
+            R.pa[kMaxPlanes + NA + i] = pe.a; R.pb[kMaxPlanes + NA + i] = pe.b; R.pc[kMaxPlanes + NA + i] = pe.c;
         }
     }
     return box;
 }
 
-// Clip-space fan triangle -> screen -> record.
+// Write a set-up triangle as record `rec` of `sink`: head, planes in the order z?, invw?, avar[nA], pvar[nP]
+// (one float4 (a, b, c, 0) each), span halves.
 template <int NA, int NP>
-SWR_HD Box16 emitClipTriangle(const GeomArgs &g, uint32_t rec, uint32_t ordinal,
-                              CVert<NA, NP> a, CVert<NA, NP> b, CVert<NA, NP> c)
+SWR_HD void storeTriangle(const GeomArgs &g, const RecordSink &sink, uint32_t rec, const TriRecord<NA, NP> &R)
+{
+    float4 *hd = sink.head + (size_t)rec * 3;
+    hd[0] = R.h0; hd[1] = R.h1; hd[2] = R.h2;
+    float4 *pp4 = reinterpret_cast<float4 *>(sink.params + (size_t)rec * g.paramStride);
+    if (g.useZ) *pp4++ = mkf4(R.pa[0], R.pb[0], R.pc[0], 0.0f);
+    if (g.useW || g.nP > 0) *pp4++ = mkf4(R.pa[1], R.pb[1], R.pc[1], 0.0f);
+#pragma unroll
+    for (int i = 0; i < NA; ++i)
+        if (i < g.nA) *pp4++ = mkf4(R.pa[kMaxPlanes + i], R.pb[kMaxPlanes + i], R.pc[kMaxPlanes + i], 0.0f);
+#pragma unroll
+    for (int i = 0; i < NP; ++i)
+        if (i < g.nP) *pp4++ = mkf4(R.pa[kMaxPlanes + NA + i], R.pb[kMaxPlanes + NA + i], R.pc[kMaxPlanes + NA + i], 0.0f);
+    if (R.span) {
+        float4 *sp = sink.span + (size_t)rec * 3;
+        sp[0] = mkf4(R.bot.vx, R.bot.vy, R.bot.inv1, R.bot.inv2);
+        sp[1] = mkf4(R.top.vx, R.top.vy, R.top.inv1, R.top.inv2);
+        sp[2] = mkf4(u2f((uint32_t)R.bot.y0), u2f((uint32_t)R.bot.y1), u2f((uint32_t)R.top.y0), u2f((uint32_t)R.top.y1));
+    }
+}
+
+// Clip-space fan triangle -> screen -> set-up record.
+template <int NA, int NP, bool SPAN = true>
+SWR_HD Box16 setupClipTriangle(const GeomArgs &g, uint32_t ordinal, CVert<NA, NP> a, CVert<NA, NP> b, CVert<NA, NP> c, TriRecord<NA, NP> &R)
 {
     toScreen(g, a);
     toScreen(g, b);
     toScreen(g, c);
-    return emitScreenTriangle(g, rec, ordinal, true, a, b, c);
+    return setupScreenTriangle<NA, NP, SPAN>(g, ordinal, true, a, b, c, R);
+}
+
+// One-call forms (sequential hosts: tests/hostcheck, the raster-list kernel): set up and store as record `rec`.
+template <int NA, int NP>
+SWR_HD Box16 emitScreenTriangle(const GeomArgs &g, const RecordSink &sink, uint32_t rec, uint32_t ordinal, bool doCull,
+                                const CVert<NA, NP> &s0, const CVert<NA, NP> &s1, const CVert<NA, NP> &s2)
+{
+    TriRecord<NA, NP> R;
+    const Box16 box = setupScreenTriangle(g, ordinal, doCull, s0, s1, s2, R);
+    if (box.x0 <= box.x1) storeTriangle(g, sink, rec, R);
+    return box;
+}
+template <int NA, int NP>
+SWR_HD Box16 emitClipTriangle(const GeomArgs &g, const RecordSink &sink, uint32_t rec, uint32_t ordinal,
+                              const CVert<NA, NP> &a, const CVert<NA, NP> &b, const CVert<NA, NP> &c)
+{
+    TriRecord<NA, NP> R;
+    const Box16 box = setupClipTriangle(g, ordinal, a, b, c, R);
+    if (box.x0 <= box.x1) storeTriangle(g, sink, rec, R);
+    return box;
 }
 
 // Rasterizer.h:144-147
@@ -439,40 +483,42 @@ SWR_HD bool scissorTest(int minX, int minY, int maxX, int maxY, float x, float y
 
 constexpr int kMaxLineSteps = 1 << 17;   // longer DDA walks cannot touch a <= 32767-pixel screen meaningfully
 
-// Screen-space line -> record (Rasterizer.h:175-222).  head0 = {x0, y0, stepx, stepy},
-// head1 = {steps, ordinal}; params = (start, step) pairs of z?, w?, avar[], pvar[].
+// Screen-space line: footprint (Rasterizer.h:175-222).  steps = 0 with a dead box when nothing is drawn;
+// *tooLong is set for walks beyond kMaxLineSteps (dropped, reported by swr_finish).
 template <int NA, int NP>
-SWR_HD Box16 emitScreenLine(const GeomArgs &g, uint32_t rec, uint32_t ordinal, const CVert<NA, NP> &v0, const CVert<NA, NP> &v1)
+SWR_HD Box16 setupScreenLine(const GeomArgs &g, const CVert<NA, NP> &v0, const CVert<NA, NP> &v1, int &steps, bool &tooLong)
 {
-    if (g.dbgVerts) {
-        float *d = g.dbgVerts + (size_t)rec * 12;
-        d[0] = v0.x; d[1] = v0.y; d[2] = v0.z; d[3] = v0.w;
-        d[4] = v1.x; d[5] = v1.y; d[6] = v1.z; d[7] = v1.w;
-        d[8] = d[9] = d[10] = d[11] = 0.0f;
-    }
     const int ix0 = f2i(v0.x), iy0 = f2i(v0.y), ix1 = f2i(v1.x), iy1 = f2i(v1.y);
     const int adx = ix1 > ix0 ? ix1 - ix0 : ix0 - ix1;
     const int ady = iy1 > iy0 ? iy1 - iy0 : iy0 - iy1;
-    const int steps = imax(adx, ady);
+    steps = imax(adx, ady);
+    tooLong = false;
     if (steps <= 0) return deadBox();
-    if (steps > kMaxLineSteps) {
-#if defined(__CUDA_ARCH__)
-        atomicOr(g.errorFlag, 2u);
-        atomicOr(g.errorFlag + 1, 2u);      // sticky copy, reported by swr_finish
-#endif
-        return deadBox();
-    }
-    // fragments must pass the float scissor test, so the footprint is inside the scissor;
-    // +-2 pixels absorb the drift of the repeated additions
-    Box16 box = makeBox(imax(imin(ix0, ix1) - 2, g.scMinX), imax(imin(iy0, iy1) - 2, g.scMinY),
-                        imin(imax(ix0, ix1) + 2, g.scMaxX - 1), imin(imax(iy0, iy1) + 2, g.scMaxY - 1));
-    if (box.x0 > box.x1) return box;
-    if (!boxTouchesOwnedTile(box, g.tileShift, g.tilesX, g.tilesY, g.rank, g.world)) return deadBox();
+    if (steps > kMaxLineSteps) { tooLong = true; return deadBox(); }
+    // Fragments must pass the float scissor test, so the footprint is inside the scissor.  The walk adds the rounded
+    // step `steps` times: each addition is off by at most half an ulp of the running coordinate, and the step itself by
+    // half an ulp of its own value times the number of additions, so position k lies within
+    // (steps + 1) * ulp(max |coordinate|) of the straight line between the end points -- the margin below.
+    float mag = fabs32(v0.x);
+    mag = fabs32(v0.y) > mag ? fabs32(v0.y) : mag;
+    mag = fabs32(v1.x) > mag ? fabs32(v1.x) : mag;
+    mag = fabs32(v1.y) > mag ? fabs32(v1.y) : mag;
+    const float drift = i2f(steps + 1) * mag * (1.0f / 8388608.0f);        // (steps + 1) * 2^-23 * max|coordinate| >= (steps + 1) ulps
+    const int margin = drift < 30000.0f ? f2i(drift) + 2 : 32767;
+    return makeBox(imax(imin(ix0, ix1) - margin, g.scMinX), imax(imin(iy0, iy1) - margin, g.scMinY),
+                   imin(imax(ix0, ix1) + margin, g.scMaxX - 1), imin(imax(iy0, iy1) + margin, g.scMaxY - 1));
+}
+
+// head0 = {x0, y0, stepx, stepy}, head1 = {steps, ordinal}; params = (start, step) pairs of z?, w?, avar[], pvar[].
+template <int NA, int NP>
+SWR_HD void storeLine(const GeomArgs &g, const RecordSink &sink, uint32_t rec, uint32_t ordinal, int steps,
+                      const CVert<NA, NP> &v0, const CVert<NA, NP> &v1)
+{
     const float fs = i2f(steps);
-    float4 *hd = g.head + (size_t)rec * 3;
+    float4 *hd = sink.head + (size_t)rec * 3;
     hd[0] = mkf4(v0.x, v0.y, fdiv(fsub(v1.x, v0.x), fs), fdiv(fsub(v1.y, v0.y), fs));
     hd[1] = mkf4(u2f((uint32_t)steps), u2f(ordinal), 0.0f, 0.0f);
-    float *pp = g.params + (size_t)rec * g.paramStride;
+    float *pp = sink.params + (size_t)rec * g.paramStride;
     if (g.useZ) { pp[0] = v0.z; pp[1] = fdiv(fsub(v1.z, v0.z), fs); pp += 2; }
     if (g.useW) { pp[0] = v0.w; pp[1] = fdiv(fsub(v1.w, v0.w), fs); pp += 2; }
 #pragma unroll
@@ -481,27 +527,24 @@ SWR_HD Box16 emitScreenLine(const GeomArgs &g, uint32_t rec, uint32_t ordinal, c
 #pragma unroll
     for (int i = 0; i < NP; ++i)
         if (i < g.nP) { pp[0] = v0.p[i]; pp[1] = fdiv(fsub(v1.p[i], v0.p[i]), fs); pp += 2; }
-    return box;
 }
 
-// Screen-space point -> record (Rasterizer.h:149-173).
+// Screen-space point: footprint (Rasterizer.h:149-173).
 template <int NA, int NP>
-SWR_HD Box16 emitScreenPoint(const GeomArgs &g, uint32_t rec, uint32_t ordinal, const CVert<NA, NP> &v)
+SWR_HD Box16 setupScreenPoint(const GeomArgs &g, const CVert<NA, NP> &v)
 {
-    if (g.dbgVerts) {
-        float *d = g.dbgVerts + (size_t)rec * 12;
-        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
-        for (int i = 4; i < 12; ++i) d[i] = 0.0f;
-    }
     if (!scissorTest(g.scMinX, g.scMinY, g.scMaxX, g.scMaxY, v.x, v.y)) return deadBox();
     const int ix = f2i(v.x), iy = f2i(v.y);
-    Box16 box = makeBox(ix, iy, ix, iy);
-    if (box.x0 > box.x1) return box;
-    if (!boxTouchesOwnedTile(box, g.tileShift, g.tilesX, g.tilesY, g.rank, g.world)) return deadBox();
-    float4 *hd = g.head + (size_t)rec * 3;
+    return makeBox(ix, iy, ix, iy);
+}
+
+template <int NA, int NP>
+SWR_HD void storePoint(const GeomArgs &g, const RecordSink &sink, uint32_t rec, uint32_t ordinal, const CVert<NA, NP> &v)
+{
+    float4 *hd = sink.head + (size_t)rec * 3;
     hd[0] = mkf4(v.x, v.y, 0.0f, 0.0f);
     hd[1] = mkf4(0.0f, u2f(ordinal), 0.0f, 0.0f);
-    float *pp = g.params + (size_t)rec * g.paramStride;
+    float *pp = sink.params + (size_t)rec * g.paramStride;
     if (g.useZ) { pp[0] = v.z; pp += 1; }
     if (g.useW) { pp[0] = v.w; pp += 1; }
 #pragma unroll
@@ -510,12 +553,12 @@ SWR_HD Box16 emitScreenPoint(const GeomArgs &g, uint32_t rec, uint32_t ordinal, 
 #pragma unroll
     for (int i = 0; i < NP; ++i)
         if (i < g.nP) { pp[0] = v.p[i]; pp += 1; }
-    return box;
 }
 
-// One input line: VertexProcessor.cpp:167-215 + LineClipper.cpp:30-56.
+// One input line in clip space: VertexProcessor.cpp:167-215 + LineClipper.cpp:30-56.  Returns false when the line is
+// clipped away; else a, b are the screen-space end points.
 template <int NA, int NP>
-SWR_HD Box16 emitClipLine(const GeomArgs &g, uint32_t rec, uint32_t ordinal, const CVert<NA, NP> &c0, const CVert<NA, NP> &c1)
+SWR_HD bool clipLineToScreen(const GeomArgs &g, const CVert<NA, NP> &c0, const CVert<NA, NP> &c1, CVert<NA, NP> &a, CVert<NA, NP> &b)
 {
     const int m0 = outcode(c0.x, c0.y, c0.z, c0.w), m1 = outcode(c1.x, c1.y, c1.z, c1.w);
     const int mask = m0 | m1;
@@ -525,7 +568,7 @@ SWR_HD Box16 emitClipLine(const GeomArgs &g, uint32_t rec, uint32_t ordinal, con
         const float d0 = planeDist(pl, c0.x, c0.y, c0.z, c0.w);
         const float d1 = planeDist(pl, c1.x, c1.y, c1.z, c1.w);
         const bool n0 = d0 < 0, n1 = d1 < 0;
-        if (n0 && n1) return deadBox();
+        if (n0 && n1) return false;
         if (n0) {
             const float t = fdiv(-d0, fsub(d1, d0));
             t0 = t0 < t ? t : t0;                           // std::max(t0, t)
@@ -534,12 +577,38 @@ SWR_HD Box16 emitClipLine(const GeomArgs &g, uint32_t rec, uint32_t ordinal, con
             t1 = t < t1 ? t : t1;                           // std::min(t1, t)
         }
     }
-    CVert<NA, NP> a = c0, b = c1;
+    a = c0; b = c1;
     if (m0) lerpVert(a, c0, c1, t0);
     if (m1) lerpVert(b, c0, c1, t1);
     toScreen(g, a);
     toScreen(g, b);
-    return emitScreenLine(g, rec, ordinal, a, b);
+    return true;
+}
+
+// One-call forms for sequential hosts.
+template <int NA, int NP>
+SWR_HD Box16 emitScreenLine(const GeomArgs &g, const RecordSink &sink, uint32_t rec, uint32_t ordinal, const CVert<NA, NP> &v0, const CVert<NA, NP> &v1)
+{
+    int steps;
+    bool tooLong;
+    const Box16 box = setupScreenLine(g, v0, v1, steps, tooLong);
+    if (tooLong) { sink.errorFlag[0] |= 2u; sink.errorFlag[1] |= 2u; }
+    if (box.x0 <= box.x1) storeLine(g, sink, rec, ordinal, steps, v0, v1);
+    return box;
+}
+template <int NA, int NP>
+SWR_HD Box16 emitClipLine(const GeomArgs &g, const RecordSink &sink, uint32_t rec, uint32_t ordinal, const CVert<NA, NP> &c0, const CVert<NA, NP> &c1)
+{
+    CVert<NA, NP> a, b;
+    if (!clipLineToScreen(g, c0, c1, a, b)) return deadBox();
+    return emitScreenLine(g, sink, rec, ordinal, a, b);
+}
+template <int NA, int NP>
+SWR_HD Box16 emitScreenPoint(const GeomArgs &g, const RecordSink &sink, uint32_t rec, uint32_t ordinal, const CVert<NA, NP> &v)
+{
+    const Box16 box = setupScreenPoint(g, v);
+    if (box.x0 <= box.x1) storePoint(g, sink, rec, ordinal, v);
+    return box;
 }
 
 #if defined(__CUDACC__)
@@ -561,54 +630,69 @@ SWR_D void shadeVertex(const GeomArgs &g, int index, CVert<VS::AVarCount, VS::PV
     for (int i = 0; i < VS::PVarCount; ++i) o.p[i] = out.pvar[i];
 }
 
-// Union of the warp's boxes -> gbox[group]; mark every screen tile the union touches in the
-// tile x chunk bitmap.
-SWR_D void publishGroup(const GeomArgs &g, Box16 box, uint32_t group, uint32_t chunk)
+// Mark every screen tile of `rank`'s partition that the group box (x0, y0)-(x1, y1) touches in that rank's
+// tile x chunk bitmap (called by a whole warp: the lanes share the tiles).  The update is a fire-and-forget
+// reduction (no NVLink round trip when the bitmap is a peer's); a local bitmap is read first, since most groups of a
+// batch find their bit already set.
+SWR_D void markTiles(const GeomArgs &g, const RecordSink &sink, int rank, bool local, uint32_t chunk, int x0, int y0, int x1, int y1)
 {
-    // warp-wide min / max in one instruction each (redux.sync) instead of four 5-step shuffle trees
-    const int x0 = __reduce_min_sync(0xffffffffu, (int)box.x0), y0 = __reduce_min_sync(0xffffffffu, (int)box.y0);
-    const int x1 = __reduce_max_sync(0xffffffffu, (int)box.x1), y1 = __reduce_max_sync(0xffffffffu, (int)box.y1);
-    const int lane = threadIdx.x & 31;
-    if (lane == 0) {
-        Box16 u; u.x0 = (int16_t)x0; u.y0 = (int16_t)y0; u.x1 = (int16_t)x1; u.y1 = (int16_t)y1;
-        g.gbox[group] = u;
-    }
     if (x0 > x1) return;
     const int tx0 = x0 >> g.tileShift, ty0 = y0 >> g.tileShift;
     const int tx1 = min(x1 >> g.tileShift, g.tilesX - 1), ty1 = min(y1 >> g.tileShift, g.tilesY - 1);
     if (tx0 > tx1 || ty0 > ty1) return;
+    const int lane = threadIdx.x & 31;
     const int nx = tx1 - tx0 + 1, nt = nx * (ty1 - ty0 + 1);
     const uint32_t bit = 1u << (chunk & 31);
     const bool oneRow = ty0 == ty1, oneCol = tx0 == tx1;     // the usual shapes: no integer division for them
     for (int i = lane; i < nt; i += 32) {
-        const int tile = oneRow ? ty0 * g.tilesX + tx0 + i : oneCol ? (ty0 + i) * g.tilesX + tx0 : (ty0 + i / nx) * g.tilesX + tx0 + i % nx;
-        uint32_t *wp = g.tilemap + (size_t)tile * g.chunkWords + (chunk >> 5);
-        if (!(*(volatile uint32_t *)wp & bit)) atomicOr(wp, bit);
+        const int ty = oneRow ? ty0 : oneCol ? ty0 + i : ty0 + i / nx;
+        const int tx = oneRow ? tx0 + i : oneCol ? tx0 : tx0 + i % nx;
+        if (!tileOwned(tx, ty, rank, g.world)) continue;
+        uint32_t *wp = sink.tilemap + (size_t)(ty * g.tilesX + tx) * g.chunkWords + (chunk >> 5);
+        if (local && (*(volatile uint32_t *)wp & bit)) continue;
+        atomicOr(wp, bit);                                   // result unused: compiles to RED
     }
 }
 
 #ifndef SWR_GEOM_MINB
-#define SWR_GEOM_MINB 4      // <= 64 registers: four 256-thread CTAs per SM (measured: 5 or 6 CTAs with spills are slower)
+#define SWR_GEOM_MINB 3      // <= 80 registers: three 256-thread CTAs per SM (measured: with four the record a thread holds until its
+                             // slot is known spills; C5 -6 %, C2 -4 %, C3 equal)
 #endif
-template <class VS>
+
+// Batch run by CTA `block` of a launch: all batches in turn, or -- sharded -- the batches of this rank.
+SWR_D int batchOfBlock(const GeomArgs &g, int block)
+{
+    if (!g.shard) return block;
+    return ((block / kShardBatches) * g.world + g.rank) * kShardBatches + block % kShardBatches;
+}
+
+// MODE = draw mode, SPAN = false when the raster mode is known to be Block (no span state is carried): both are
+// launch-time constants, and as template parameters they keep the registers that live across the compaction
+// barrier down to what the mode really needs.
+template <class VS, int MODE, bool SPAN>
 __global__ void __launch_bounds__(kGeomThreads, SWR_GEOM_MINB) geometryKernel(const GeomArgs g)
 {
     constexpr int NA = VS::AVarCount, NP = VS::PVarCount;
     typedef CVert<NA, NP> V;
     constexpr int kMaxExtraGroups = kBatch * (kMaxFan - 1) / kGroup;
+    constexpr int kWarps = kGeomThreads / 32;
 
     __shared__ uint16_t sExtraCnt[kBatch];     // fan extras per primitive of this batch
     __shared__ uint16_t sExtraOfs[kBatch];     // exclusive prefix in primitive order
-    __shared__ uint32_t sWarpSum[kGeomThreads / 32];
+    __shared__ uint32_t sWarpSum[kWarps];
     __shared__ uint32_t sExtraBase, sExtraTotal;
     __shared__ int sGx0[kMaxExtraGroups], sGy0[kMaxExtraGroups], sGx1[kMaxExtraGroups], sGy1[kMaxExtraGroups];
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int batch = blockIdx.x;
+    const int batch = batchOfBlock(g, blockIdx.x);
     const int primBase = batch * kBatch;
+    if (primBase >= g.numPrims) return;
     const int cnt = min(kBatch, g.numPrims - primBase);
     const uint32_t ord0 = (g.firstBatch + (uint32_t)batch) * SWR_ORDINAL_STRIDE;
-    const int per = g.drawMode + 1;
+    constexpr int per = MODE + 1;
+    const int world = g.world;
+    // replicated geometry: only the records of this rank's tiles are kept
+    const uint32_t keepMask = g.shard ? (1u << world) - 1u : (1u << g.rank);
     bool anyExtra = false;
 
     // the next round's indices are fetched while the current round computes (the vertex fetch
@@ -630,13 +714,17 @@ __global__ void __launch_bounds__(kGeomThreads, SWR_GEOM_MINB) geometryKernel(co
     for (int r = 0; r < kRounds; ++r) {
         if (r + 1 < kRounds) fetch(r + 1, nxt);
         const int slot = r * kGeomThreads + tid;
-        const uint32_t rec = (uint32_t)(primBase + slot);
+        const uint32_t group = (uint32_t)(primBase + slot) >> 5;      // the 32 slots this warp handles in this round
         Box16 box = deadBox();
         int extras = 0;
+        const uint32_t ordinal = ord0 + (uint32_t)slot;
+        TriRecord<NA, NP> R;
+        V la, lb;                                  // line end points / the point, in screen space
+        int steps = 0;
+        R.span = false;
         if (slot < cnt) {
             const int32_t ip[3] = { cur[0], cur[1], cur[2] };
-            const uint32_t ordinal = ord0 + (uint32_t)slot;
-            if (g.drawMode == SWR_DRAW_TRIANGLE) {
+            if (MODE == SWR_DRAW_TRIANGLE) {
                 V v0, v1, v2;
                 shadeVertex<VS>(g, ip[0], v0);
                 shadeVertex<VS>(g, ip[1], v1);
@@ -645,7 +733,7 @@ __global__ void __launch_bounds__(kGeomThreads, SWR_GEOM_MINB) geometryKernel(co
                           m2 = outcode(v2.x, v2.y, v2.z, v2.w);
                 const int mask = m0 | m1 | m2;
                 if (mask == 0) {
-                    box = emitClipTriangle<NA, NP>(g, rec, ordinal, v0, v1, v2);
+                    box = setupClipTriangle<NA, NP, SPAN>(g, ordinal, v0, v1, v2, R);
                 } else if ((mask & -mask) & (m0 & m1 & m2)) {
                     // Trivial reject, exactly as the reference computes it: the FIRST plane it clips
                     // against (lowest flagged bit, VertexProcessor.cpp:237-242) has all three original
@@ -655,38 +743,75 @@ __global__ void __launch_bounds__(kGeomThreads, SWR_GEOM_MINB) geometryKernel(co
                 } else {
                     V a[kMaxPoly], b[kMaxPoly], *poly;      // rare path: polygons live in local memory
                     a[0] = v0; a[1] = v1; a[2] = v2;
-                    const int n = clipTriangle<NA, NP>(a, b, mask, &poly);
+                    bool overflow = false;
+                    const int n = clipTriangle<NA, NP>(a, b, mask, &poly, &overflow);
+                    if (overflow) { atomicOr(g.sink[g.rank].errorFlag, 4u); atomicOr(g.sink[g.rank].errorFlag + 1, 4u); }
                     if (n >= 3) {
-                        box = emitClipTriangle<NA, NP>(g, rec, ordinal, poly[0], poly[1], poly[2]);
+                        box = setupClipTriangle<NA, NP, SPAN>(g, ordinal, poly[0], poly[1], poly[2], R);
                         extras = n - 3;
                     }
                 }
-            } else if (g.drawMode == SWR_DRAW_LINE) {
+            } else if (MODE == SWR_DRAW_LINE) {
                 V c0, c1;
                 shadeVertex<VS>(g, ip[0], c0);
                 shadeVertex<VS>(g, ip[1], c1);
-                box = emitClipLine<NA, NP>(g, rec, ordinal, c0, c1);
+                if (clipLineToScreen<NA, NP>(g, c0, c1, la, lb)) {
+                    bool tooLong;
+                    box = setupScreenLine<NA, NP>(g, la, lb, steps, tooLong);
+                    if (tooLong) { atomicOr(g.sink[g.rank].errorFlag, 2u); atomicOr(g.sink[g.rank].errorFlag + 1, 2u); }
+                }
             } else {
-                V c0;
-                shadeVertex<VS>(g, ip[0], c0);
-                if (outcode(c0.x, c0.y, c0.z, c0.w) == 0) {     // VertexProcessor.cpp:152-165
-                    toScreen(g, c0);
-                    box = emitScreenPoint<NA, NP>(g, rec, ordinal, c0);
+                shadeVertex<VS>(g, ip[0], la);
+                if (outcode(la.x, la.y, la.z, la.w) == 0) {     // VertexProcessor.cpp:152-165
+                    toScreen(g, la);
+                    box = setupScreenPoint<NA, NP>(g, la);
                 }
             }
         }
-        g.bbox[rec] = box;
         sExtraCnt[slot] = (uint16_t)extras;
         anyExtra |= extras > 0;
-        publishGroup(g, box, rec >> 5, 2u * (uint32_t)batch);
+
+        // ---- per destination rank: the surviving records of the group, compacted to the front of the group's 32
+        // slots in submission order (ballot + popcount: the warps never wait for each other), their count, the
+        // union of their boxes and the tiles it touches.  Slots behind the count are never written, nor read.
+        const uint32_t dm = boxOwnerMask(box, g.tileShift, g.tilesX, g.tilesY, world) & keepMask;
+        const uint32_t anyD = __reduce_or_sync(0xffffffffu, dm);
+        if (lane < world && ((keepMask >> lane) & 1u) && !((anyD >> lane) & 1u)) {
+            g.sink[lane].gbox[group] = deadBox();             // nothing of this group concerns rank `lane`
+            g.sink[lane].gcnt[group] = 0;
+        }
+        for (uint32_t m = anyD; m; m &= m - 1) {
+            const int d = __ffs((int)m) - 1;
+            const bool mine = (dm >> d) & 1u;
+            const uint32_t b = __ballot_sync(0xffffffffu, mine);
+            const int x0 = __reduce_min_sync(0xffffffffu, mine ? (int)box.x0 : 32767), y0 = __reduce_min_sync(0xffffffffu, mine ? (int)box.y0 : 32767);
+            const int x1 = __reduce_max_sync(0xffffffffu, mine ? (int)box.x1 : -32768), y1 = __reduce_max_sync(0xffffffffu, mine ? (int)box.y1 : -32768);
+            const RecordSink &sk = g.sink[d];
+            if (mine) {
+                const uint32_t rec = (group << 5) + (uint32_t)__popc(b & ((1u << lane) - 1u));
+                sk.bbox[rec] = box;
+                if (MODE == SWR_DRAW_TRIANGLE) storeTriangle<NA, NP>(g, sk, rec, R);
+                else if (MODE == SWR_DRAW_LINE) storeLine<NA, NP>(g, sk, rec, ordinal, steps, la, lb);
+                else storePoint<NA, NP>(g, sk, rec, ordinal, la);
+            }
+            if (lane == 0) {
+                Box16 u; u.x0 = (int16_t)x0; u.y0 = (int16_t)y0; u.x1 = (int16_t)x1; u.y1 = (int16_t)y1;
+                sk.gbox[group] = u;
+                sk.gcnt[group] = (uint8_t)__popc(b);
+            }
+            markTiles(g, sk, d, d == g.rank, 2u * (uint32_t)batch, x0, y0, x1, y1);
+        }
         cur[0] = nxt[0]; cur[1] = nxt[1]; cur[2] = nxt[2];
     }
+    // groups of a short last batch that no warp visited: the binning reads all ceil(cnt / 32) groups of a chunk
+    // (all 32 warps-rounds ran above, so every group < 32 was written; nothing to do)
 
-    // ---- clipper fan extras: appended behind the batch's original slots, in primitive order
-    if (!__syncthreads_or(anyExtra)) {
-        if (tid == 0) g.extra[batch] = make_uint2(0u, 0u);
-        return;
-    }
+    const bool haveExtras = __syncthreads_or(anyExtra);
+    if (tid < world && ((keepMask >> tid) & 1u) && (MODE != SWR_DRAW_TRIANGLE || !haveExtras)) g.sink[tid].extra[batch] = make_uint2(0u, 0u);
+    if (MODE != SWR_DRAW_TRIANGLE || !haveExtras) return;
+
+    // ---- clipper fan extras: appended behind the batch's original slots, in primitive order.  They keep one slot
+    // each (no compaction): every rank gets the whole range of boxes, dead where the triangle is not its business.
     {   // exclusive scan of sExtraCnt over the 1024 slots: thread t owns slots 4t..4t+3
         uint32_t c0 = sExtraCnt[4 * tid], c1 = sExtraCnt[4 * tid + 1], c2 = sExtraCnt[4 * tid + 2], c3 = sExtraCnt[4 * tid + 3];
         uint32_t sum = c0 + c1 + c2 + c3, incl = sum;
@@ -708,16 +833,21 @@ __global__ void __launch_bounds__(kGeomThreads, SWR_GEOM_MINB) geometryKernel(co
             const uint32_t total = ex + sum;
             const uint32_t padded = (total + kGroup - 1) & ~(uint32_t)(kGroup - 1);
             uint32_t b0 = atomicAdd(g.extraAlloc, padded);
-            if (b0 + padded > g.extrasEnd) { atomicOr(g.errorFlag, 1u); atomicOr(g.errorFlag + 1, 1u); b0 = 0xffffffffu; }
+            if (b0 + padded > g.extrasEnd) {             // scratch exhausted: the draw is void on every rank
+                for (int d = 0; d < world; ++d)
+                    if ((keepMask >> d) & 1u) { atomicOr(g.sink[d].errorFlag, 1u); atomicOr(g.sink[d].errorFlag + 1, 1u); }
+                b0 = 0xffffffffu;
+            }
             sExtraBase = b0;
             sExtraTotal = total;
-            g.extra[batch] = (b0 == 0xffffffffu) ? make_uint2(0u, 0u) : make_uint2(b0, total);
         }
         for (int i = tid; i < kMaxExtraGroups; i += kGeomThreads) { sGx0[i] = 32767; sGy0[i] = 32767; sGx1[i] = -32768; sGy1[i] = -32768; }
         __syncthreads();
     }
     const uint32_t ebase = sExtraBase, etotal = sExtraTotal;
-    if (ebase == 0xffffffffu) return;                       // scratch exhausted: flagged, draw is void
+    if (tid < world && ((keepMask >> tid) & 1u))
+        g.sink[tid].extra[batch] = (ebase == 0xffffffffu) ? make_uint2(0u, 0u) : make_uint2(ebase, etotal);
+    if (ebase == 0xffffffffu) return;                       // flagged, draw is void
 
     for (int r = 0; r < kBatch / kGeomThreads; ++r) {
         const int slot = r * kGeomThreads + tid;
@@ -731,13 +861,20 @@ __global__ void __launch_bounds__(kGeomThreads, SWR_GEOM_MINB) geometryKernel(co
         shadeVertex<VS>(g, ip[2], a[2]);
         const int mask = outcode(a[0].x, a[0].y, a[0].z, a[0].w) | outcode(a[1].x, a[1].y, a[1].z, a[1].w) |
                          outcode(a[2].x, a[2].y, a[2].z, a[2].w);
-        const int n = clipTriangle<NA, NP>(a, b, mask, &poly);
+        const int n = clipTriangle<NA, NP>(a, b, mask, &poly, nullptr);
         for (int k = 1; k + 2 < n; ++k) {                   // fan (p0, p[k+1], p[k+2]), VertexProcessor.cpp:257-261
             const uint32_t e = ofs + (uint32_t)(k - 1);
             const uint32_t rec = ebase + e;
-            const Box16 box = emitClipTriangle<NA, NP>(g, rec, ord0 + (uint32_t)cnt + e, poly[0], poly[k + 1], poly[k + 2]);
-            g.bbox[rec] = box;
-            if (box.x0 <= box.x1) {
+            TriRecord<NA, NP> R;
+            const Box16 box = setupClipTriangle<NA, NP, SPAN>(g, ord0 + (uint32_t)cnt + e, poly[0], poly[k + 1], poly[k + 2], R);
+            const uint32_t dm = boxOwnerMask(box, g.tileShift, g.tilesX, g.tilesY, world) & keepMask;
+            for (int d = 0; d < world; ++d) {
+                if (!((keepMask >> d) & 1u)) continue;
+                const bool mine = (dm >> d) & 1u;
+                g.sink[d].bbox[rec] = mine ? box : deadBox();
+                if (mine) storeTriangle<NA, NP>(g, g.sink[d], rec, R);
+            }
+            if (dm) {
                 atomicMin(&sGx0[e >> 5], (int)box.x0); atomicMin(&sGy0[e >> 5], (int)box.y0);
                 atomicMax(&sGx1[e >> 5], (int)box.x1); atomicMax(&sGy1[e >> 5], (int)box.y1);
             }
@@ -745,11 +882,18 @@ __global__ void __launch_bounds__(kGeomThreads, SWR_GEOM_MINB) geometryKernel(co
     }
     __syncthreads();
     const uint32_t padded = (etotal + kGroup - 1) & ~(uint32_t)(kGroup - 1);
-    for (uint32_t e = etotal + tid; e < padded; e += kGeomThreads) g.bbox[ebase + e] = deadBox();
+    // group boxes of the extras (one union box per group, shared by all ranks: each rank marks only its own tiles)
     const int ngroups = (int)(padded >> 5);
-    for (int gi = wid; gi < ngroups; gi += kGeomThreads / 32) {
-        Box16 u; u.x0 = (int16_t)sGx0[gi]; u.y0 = (int16_t)sGy0[gi]; u.x1 = (int16_t)sGx1[gi]; u.y1 = (int16_t)sGy1[gi];
-        publishGroup(g, u, (ebase >> 5) + (uint32_t)gi, 2u * (uint32_t)batch + 1u);
+    for (int i = wid; i < ngroups * world; i += kWarps) {
+        const int gi = i / world, d = i - gi * world;
+        if (!((keepMask >> d) & 1u)) continue;
+        const RecordSink &sk = g.sink[d];
+        if (lane == 0) {
+            Box16 u; u.x0 = (int16_t)sGx0[gi]; u.y0 = (int16_t)sGy0[gi]; u.x1 = (int16_t)sGx1[gi]; u.y1 = (int16_t)sGy1[gi];
+            sk.gbox[(ebase >> 5) + (uint32_t)gi] = u;
+            sk.gcnt[(ebase >> 5) + (uint32_t)gi] = (uint8_t)min(32u, etotal - (uint32_t)gi * 32u);
+        }
+        markTiles(g, sk, d, d == g.rank, 2u * (uint32_t)batch + 1u, sGx0[gi], sGy0[gi], sGx1[gi], sGy1[gi]);
     }
 }
 
@@ -758,7 +902,24 @@ void launchGeometry(const void *args, void *stream)
 {
     const GeomArgs *g = static_cast<const GeomArgs *>(args);
     const int batches = (g->numPrims + kBatch - 1) / kBatch;
-    if (batches > 0) geometryKernel<VS><<<batches, kGeomThreads, 0, (cudaStream_t)stream>>>(*g);
+    int blocks = batches;
+    if (g->shard) {
+        // runs of kShardBatches batches go round-robin to the ranks: CTAs for every run of this rank (the kernel
+        // drops the batches past the end of the pass)
+        const int runs = (batches + kShardBatches - 1) / kShardBatches;
+        const int mine = runs > g->rank ? (runs - g->rank + g->world - 1) / g->world : 0;
+        blocks = mine * kShardBatches;
+    }
+    if (blocks <= 0) return;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (g->drawMode == SWR_DRAW_TRIANGLE) {
+        if (g->rasterMode == SWR_RASTER_BLOCK) geometryKernel<VS, SWR_DRAW_TRIANGLE, false><<<blocks, kGeomThreads, 0, st>>>(*g);
+        else geometryKernel<VS, SWR_DRAW_TRIANGLE, true><<<blocks, kGeomThreads, 0, st>>>(*g);
+    } else if (g->drawMode == SWR_DRAW_LINE) {
+        geometryKernel<VS, SWR_DRAW_LINE, false><<<blocks, kGeomThreads, 0, st>>>(*g);
+    } else {
+        geometryKernel<VS, SWR_DRAW_POINT, false><<<blocks, kGeomThreads, 0, st>>>(*g);
+    }
 }
 
 template <class VS>

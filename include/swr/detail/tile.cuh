@@ -24,6 +24,7 @@
 
 #include "common.h"
 #include "geometry.cuh"
+#include "bin.cuh"
 #include "../PixelShaderBase.h"
 #include "../Uniforms.h"
 
@@ -911,8 +912,10 @@ __global__ void __launch_bounds__(kTileThreads, SWR_TILE_MINB) tileKernel(const 
             const uint32_t pr0 = pb + 4u * tid;
             uint32_t pend = 0, rec0 = 0;                     // bit k: record rec0 + k still has to be tested / queued
             if (pr0 < npairs) {
-                rec0 = gList[pr0 >> 5] * 32u + (pr0 & 31u);
-                pend = 0xfu;
+                const uint32_t ge = gList[pr0 >> 5];
+                const uint32_t n = groupCount(ge), q0 = pr0 & 31u;       // the group's records sit in its first n slots
+                rec0 = groupOf(ge) * 32u + q0;
+                pend = q0 >= n ? 0u : (n - q0 >= 4u ? 0xfu : (1u << (n - q0)) - 1u);
             }
             while (true) {
                 // (re)derive the block ranges of the pending records; after a flush this re-reads the
@@ -1067,7 +1070,7 @@ __global__ void __launch_bounds__(kTileThreads, SWR_TILE_MINB) tileKernel(const 
                 uint32_t e2 = nGroup + blockScan32((uint32_t)__popc(hits), tot2, sScan, phase);
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                    if ((hits >> k) & 1u) gList[e2++] = grp[k];
+                    if ((hits >> k) & 1u) gList[e2++] = packGroup(grp[k], t.gcnt[grp[k]]);
                 nGroup += (uint32_t)tot2;
             }
             __syncthreads();

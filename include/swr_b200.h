@@ -45,6 +45,7 @@ enum { SWR_RASTER_SPAN = 0, SWR_RASTER_BLOCK = 1, SWR_RASTER_ADAPTIVE = 2 };    
 #define SWR_MAX_POLY 12             /* clipped polygon cap (9 in general position; see oracle/swr_scene.h) */
 #define SWR_ORDINAL_STRIDE 10240u   /* emission ordinal = batch * stride + slot */
 #define SWR_MAX_TILE_MIRRORS 7
+#define SWR_MAX_RANKS 8            /* GPUs of one sort-first partition (one NVLink / NVSwitch domain) */
 #define SWR_MAX_RENDER_TARGETS 12
 #define SWR_MAX_UNIFORM_BYTES 1024
 
@@ -201,10 +202,26 @@ SWR_API int swr_ipc_get_handle(const void *device_ptr, void *handle64, int64_t *
 SWR_API int swr_ipc_open(swr_context *ctx, const void *handle64, int64_t offset, void **device_ptr);
 SWR_API int swr_ipc_close(swr_context *ctx, void *device_ptr);
 
+/* ---- sharded geometry: the vertex stage of a sort-first partition, split by batches ------------------------
+ * With swr_set_tile_partition alone every rank runs the whole vertex stage and keeps the records of its own tiles.
+ * With geometry shards each rank runs only every world-th run of 16 batches and writes every surviving record
+ * straight into the scratch of the ranks whose tiles it touches -- plain stores through peer mappings (NVLink), in
+ * the reference's emission order per destination -- followed by a flag barrier between the GPUs (no NCCL call on
+ * the path).  Set-up, identical on every rank: (1) swr_shared_scratch_create(bytes): one allocation that holds the
+ * per-pass scratch (same `bytes`, render-target size, tile size and scratch limit on every rank: the ranks address
+ * each other's arrays by offset); (2) export it with swr_ipc_get_handle, exchange the handles, map the peers' with
+ * swr_ipc_open; (3) a host barrier (all arenas exist and are zeroed); (4) swr_set_geometry_shards(rank, world,
+ * arenas) with arenas[r] = rank r's scratch as mapped HERE (own entry ignored).  Every rank must then issue the same
+ * sequence of draws and swr_peer_barrier calls.  world = 1 switches it off. */
+SWR_API int swr_shared_scratch_create(swr_context *ctx, size_t bytes, void **base);
+SWR_API int swr_set_geometry_shards(swr_context *ctx, int rank, int world, void *const *arenas);
+/* Stream-ordered barrier between the ranks of the partition (one 32-thread kernel: release stores to the peers'
+ * flag words, acquire spin on the own ones).  What every rank enqueued before it -- draws, tile mirror stores -- is
+ * complete and visible on all ranks before anything enqueued after it starts.  The frame loop of a partition calls
+ * it once per frame (composite complete); it also pre-pays the barrier the next draw would otherwise need. */
+SWR_API int swr_peer_barrier(swr_context *ctx);
+
 /* ---- debugging ------------------------------------------------------------------------------ */
-/* Copies the geometry stage's records of the last pass to host arrays (any may be NULL):
- * bbox: 4 x int16 per record, ordinal: uint32 per record, verts: 12 floats (3 x xyzw screen space). */
-SWR_API int swr_debug_enable_stream(swr_context *ctx, int enable);
 /* Per-tile timing of the next draws: after a draw, swr_debug_read_tile_stats copies 16 uint32 per tile
  * {start ns (low 32 bits of %globaltimer), duration ns, primitives queued, fragments, clocks/16 of thread 0 in the
  * pre-test / coverage / shading phases, flushes, clocks/16 in the flush prologue / record binning / chunk + group
@@ -212,7 +229,6 @@ SWR_API int swr_debug_enable_stream(swr_context *ctx, int enable);
  * -DSWR_TILE_STATS=1 (the clocks cost ~2 %); the stock build returns an error from the enable call. */
 SWR_API int swr_debug_enable_tile_stats(swr_context *ctx, int enable);
 SWR_API int64_t swr_debug_read_tile_stats(swr_context *ctx, uint32_t *out, int64_t cap_tiles);
-SWR_API int64_t swr_debug_read_stream(swr_context *ctx, int16_t *bbox, uint32_t *ordinal, float *verts, int64_t cap);
 
 #ifdef __cplusplus
 }

@@ -72,14 +72,15 @@ SYMBOLS = [
     ("swr_pack_tiles", C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     ("swr_unpack_tiles", C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     ("swr_owned_tile_count", C.c_int64, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
-    ("swr_debug_enable_stream", C.c_int, [_P, C.c_int]),
     ("swr_set_tile_mirrors", C.c_int, [_P, C.c_int, C.c_int, _P]),
     ("swr_ipc_get_handle", C.c_int, [_P, _P, C.POINTER(C.c_int64)]),
     ("swr_ipc_open", C.c_int, [_P, _P, C.c_int64, C.POINTER(C.c_void_p)]),
     ("swr_ipc_close", C.c_int, [_P, _P]),
     ("swr_debug_enable_tile_stats", C.c_int, [_P, C.c_int]),
     ("swr_debug_read_tile_stats", C.c_int64, [_P, _P, C.c_int64]),
-    ("swr_debug_read_stream", C.c_int64, [_P, _P, _P, _P, C.c_int64]),
+    ("swr_shared_scratch_create", C.c_int, [_P, C.c_size_t, C.POINTER(C.c_void_p)]),
+    ("swr_set_geometry_shards", C.c_int, [_P, C.c_int, C.c_int, _P]),
+    ("swr_peer_barrier", C.c_int, [_P]),
 ]
 
 _lib = None

@@ -138,6 +138,21 @@ class Rasterizer:
     def ipcClose(self, ptr: int):
         _lib.check(lib.swr_ipc_close(self._ctx, C.c_void_p(ptr)), "ipcClose")
 
+    def createSharedScratch(self, nbytes: int) -> int:
+        """One allocation for the per-pass scratch that the peers of a partition can map (sharded geometry)."""
+        out = C.c_void_p()
+        _lib.check(lib.swr_shared_scratch_create(self._ctx, nbytes, C.byref(out)), "createSharedScratch")
+        return int(out.value)
+
+    def setGeometryShards(self, rank: int, world: int, arenas):
+        """arenas[r] = device address of rank r's shared scratch as mapped in this process (own entry ignored)."""
+        arr = (C.c_void_p * max(len(arenas), 1))(*[C.c_void_p(int(p) if p else 0) for p in arenas])
+        _lib.check(lib.swr_set_geometry_shards(self._ctx, rank, world, arr), "setGeometryShards")
+
+    def peerBarrier(self):
+        """Stream-ordered barrier between the ranks of the partition (no NCCL call)."""
+        _lib.check(lib.swr_peer_barrier(self._ctx), "peerBarrier")
+
     def setScratchLimit(self, nbytes: int):
         _lib.check(lib.swr_set_scratch_limit(self._ctx, nbytes), "setScratchLimit")
 

@@ -76,14 +76,6 @@ struct Attrib {
     size_t bytes = 0;
 };
 
-struct Counters {               // one small device block
-    uint32_t extraAlloc;
-    uint32_t errorFlag;         // per draw: bit 0 voids the draw (tile kernel exits)
-    uint32_t stickyFlag;        // same bits, accumulated until swr_finish reports them
-    uint32_t pad;
-    unsigned long long fragments;
-};
-
 bool isDevicePointer(const void *p)
 {
     cudaPointerAttributes a;
@@ -96,15 +88,71 @@ bool isDevicePointer(const void *p)
 
 } // namespace
 
-// One set of per-pass scratch.  Two sets alternate so that the geometry kernel of pass k+1 (on the
-// auxiliary stream) overlaps the tile kernel of pass k (on the main stream).
+// One set of per-pass scratch: a single allocation ("blob") cut into the arrays of common.h by layoutOf(), plus a
+// small counter block.  Two sets alternate when the geometry kernel of pass k+1 (auxiliary stream) overlaps the tile
+// kernel of pass k (swr_set_pipeline).  With a shared scratch arena (swr_shared_scratch_create: sharded geometry,
+// the peers write into this memory) there is one set and both live inside the arena, at offsets that are the same
+// on every rank.
+struct SetLayout {
+    size_t bbox, gbox, gcnt, head, params, span, tilemap, extra, groupList, groupCount, bytes;
+};
+
+struct Counters {               // one small device block
+    uint32_t extraAlloc;
+    uint32_t errorFlag;         // per draw: bit 0 voids the draw (tile kernel exits)
+    uint32_t stickyFlag;        // same bits, accumulated until swr_finish reports them
+    uint32_t pad;
+    unsigned long long fragments;
+};
+
+constexpr size_t kArenaHeader = 4096;        // Counters at 0, barrier flags (kMaxRanks words) at kArenaFlags
+constexpr size_t kArenaFlags = 512;
+
 struct ScratchSet {
-    DevBuf bbox, gbox, head, params, span, tilemap, extra, counters, groupList, groupCount;
+    DevBuf blob, counters;
+    char *base = nullptr;               // blob.ptr, or the arena's record area
+    Counters *ctr = nullptr;
     cudaEvent_t geomDone = nullptr, tileDone = nullptr;
     bool tilePending = false, countersInit = false;
-    size_t bytes() const { return bbox.bytes + gbox.bytes + head.bytes + params.bytes + span.bytes + tilemap.bytes + extra.bytes + counters.bytes + groupList.bytes + groupCount.bytes; }
-    void release() { bbox.release(); gbox.release(); head.release(); params.release(); span.release(); tilemap.release(); extra.release(); counters.release(); groupList.release(); groupCount.release(); }
+    size_t bytes() const { return blob.bytes + counters.bytes; }
+    void release() { blob.release(); counters.release(); base = nullptr; ctr = nullptr; countersInit = false; }
 };
+
+static size_t alignUp(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static SetLayout layoutOf(size_t recCap, int paramStride, bool needSpan, size_t tiles, int chunkWords, size_t passBatches, uint32_t groupCap, bool binPass)
+{
+    SetLayout L;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { const size_t at = o; o = alignUp(o + bytes, 256); return at; };
+    L.bbox = take(recCap * sizeof(Box16) + 64);
+    L.gbox = take((recCap / kGroup + 1) * sizeof(Box16));
+    L.gcnt = take(recCap / kGroup + 1);
+    L.head = take(recCap * 48);
+    L.params = take(recCap * (size_t)paramStride * 4 + 16);
+    L.span = take(needSpan ? recCap * 48 : 0);
+    L.tilemap = take(tiles * (size_t)chunkWords * 4);
+    L.extra = take(passBatches * sizeof(uint2));
+    L.groupList = take(binPass ? tiles * (size_t)groupCap * 4 : 0);
+    L.groupCount = take(binPass ? tiles * 4 : 0);
+    L.bytes = o;
+    return L;
+}
+
+static RecordSink sinkAt(char *base, const SetLayout &L, Counters *ctr)
+{
+    RecordSink k;
+    k.bbox = reinterpret_cast<Box16 *>(base + L.bbox);
+    k.gbox = reinterpret_cast<Box16 *>(base + L.gbox);
+    k.head = reinterpret_cast<float4 *>(base + L.head);
+    k.params = reinterpret_cast<float *>(base + L.params);
+    k.span = reinterpret_cast<float4 *>(base + L.span);
+    k.tilemap = reinterpret_cast<uint32_t *>(base + L.tilemap);
+    k.gcnt = reinterpret_cast<uint8_t *>(base + L.gcnt);
+    k.extra = reinterpret_cast<uint2 *>(base + L.extra);
+    k.errorFlag = &ctr->errorFlag;
+    return k;
+}
 
 struct swr_context {
     int device = 0;
@@ -143,8 +191,15 @@ struct swr_context {
     size_t scratchLimit = (size_t)16 << 30;
 
     // scratch
-    DevBuf dbgVerts, stageIdx, l2flush, ownedIdx, tileStats;
+    DevBuf stageIdx, l2flush, ownedIdx, tileStats, arena, soVerts, soIndices, soCounts, maxIndexBuf;
     bool debugTileStats = false;
+    // sharded geometry (swr_shared_scratch_create / swr_set_geometry_shards)
+    bool shardGeometry = false;
+    char *peerArena[kMaxRanks] = {};
+    uint32_t barrierEpoch = 0;
+    uint64_t clearedKey = 0;            // layout the set's tile bitmap / counters are currently cleared for (0: dirty)
+    bool fencedSinceClear = false;      // ... and a peer barrier ran after that clear
+    int pinnedTileShift = 0;            // world > 1: the tile size of the first draw is kept (tile ownership depends on it)
     int mirrorSlot = 0, mirrorCount = 0;
     void *mirror[SWR_MAX_TILE_MIRRORS] = {};
     std::vector<std::pair<void *, void *>> ipcOpened;   // {pointer handed out, mapped base}
@@ -157,12 +212,7 @@ struct swr_context {
     bool stageUsed[2] = { false, false };
     int stageSet = 0;
     uint32_t *hostFlags = nullptr;   // pinned: error flag read-back
-    bool debugStream = false;
-
-    // last pass (debug reader)
-    int lastPassPrims = 0, lastDrawMode = 0;
-    uint32_t lastFirstBatch = 0;
-    uint32_t lastExtrasBegin = 0;
+    int lastDrawMode = 0;
 
     swr_stats stats = {};
 };
@@ -177,7 +227,8 @@ int setDevice(swr_context *c)
 
 size_t scratchBytes(const swr_context *c)
 {
-    size_t n = c->sets[0].bytes() + c->sets[1].bytes() + c->dbgVerts.bytes + c->stageIdx.bytes + c->l2flush.bytes + c->ownedIdx.bytes;
+    size_t n = c->sets[0].bytes() + c->sets[1].bytes() + c->arena.bytes + c->stageIdx.bytes + c->l2flush.bytes + c->ownedIdx.bytes +
+               c->soVerts.bytes + c->soIndices.bytes + c->soCounts.bytes;
     for (int i = 0; i < SWR_MAX_VERTEX_ATTRIBS; ++i) n += c->stageAttrib[i].bytes + c->stageAttribB[i].bytes;
     n += c->stageIdxB.bytes;
     return n;
@@ -189,13 +240,14 @@ size_t scratchBytes(const swr_context *c)
 __global__ void __launch_bounds__(kGeomThreads) rasterListKernel(const GeomArgs g)
 {
     typedef CVert<SWR_MAX_AVARS, SWR_MAX_PVARS> V;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int batch = blockIdx.x;
     const int primBase = batch * kBatch;
     const int cnt = min(kBatch, g.numPrims - primBase);
     const uint32_t ord0 = (g.firstBatch + (uint32_t)batch) * SWR_ORDINAL_STRIDE;
     const int per = g.drawMode + 1;
     const V *verts = static_cast<const V *>(g.rasterVerts);     // RasterizerVertex has exactly this layout
+    const RecordSink &sk = g.sink[g.rank];                      // every rank walks the whole list and keeps what touches its tiles
     for (int r = 0; r < kBatch / kGeomThreads; ++r) {
         const int slot = r * kGeomThreads + tid;
         const uint32_t rec = (uint32_t)(primBase + slot);
@@ -205,17 +257,26 @@ __global__ void __launch_bounds__(kGeomThreads) rasterListKernel(const GeomArgs 
             const uint32_t ordinal = ord0 + (uint32_t)slot;
             if (ip[0] != -1) {
                 if (g.drawMode == SWR_DRAW_TRIANGLE)
-                    box = emitScreenTriangle<SWR_MAX_AVARS, SWR_MAX_PVARS>(g, rec, ordinal, false, verts[ip[0]], verts[ip[1]], verts[ip[2]]);
+                    box = emitScreenTriangle<SWR_MAX_AVARS, SWR_MAX_PVARS>(g, sk, rec, ordinal, false, verts[ip[0]], verts[ip[1]], verts[ip[2]]);
                 else if (g.drawMode == SWR_DRAW_LINE)
-                    box = emitScreenLine<SWR_MAX_AVARS, SWR_MAX_PVARS>(g, rec, ordinal, verts[ip[0]], verts[ip[1]]);
+                    box = emitScreenLine<SWR_MAX_AVARS, SWR_MAX_PVARS>(g, sk, rec, ordinal, verts[ip[0]], verts[ip[1]]);
                 else
-                    box = emitScreenPoint<SWR_MAX_AVARS, SWR_MAX_PVARS>(g, rec, ordinal, verts[ip[0]]);
+                    box = emitScreenPoint<SWR_MAX_AVARS, SWR_MAX_PVARS>(g, sk, rec, ordinal, verts[ip[0]]);
+                if (!((boxOwnerMask(box, g.tileShift, g.tilesX, g.tilesY, g.world) >> g.rank) & 1u)) box = deadBox();
             }
         }
-        g.bbox[rec] = box;
-        publishGroup(g, box, rec >> 5, 2u * (uint32_t)batch);
+        sk.bbox[rec] = box;
+        // union of the warp's boxes -> group box, tiles of the union -> bitmap
+        const int x0 = __reduce_min_sync(0xffffffffu, (int)box.x0), y0 = __reduce_min_sync(0xffffffffu, (int)box.y0);
+        const int x1 = __reduce_max_sync(0xffffffffu, (int)box.x1), y1 = __reduce_max_sync(0xffffffffu, (int)box.y1);
+        if (lane == 0) {
+            Box16 u; u.x0 = (int16_t)x0; u.y0 = (int16_t)y0; u.x1 = (int16_t)x1; u.y1 = (int16_t)y1;
+            sk.gbox[rec >> 5] = u;
+            sk.gcnt[rec >> 5] = 32;                             // the list is not compacted: skipped entries are dead boxes
+        }
+        markTiles(g, sk, g.rank, true, 2u * (uint32_t)batch, x0, y0, x1, y1);
     }
-    if (tid == 0) g.extra[batch] = make_uint2(0u, 0u);
+    if (tid == 0) sk.extra[batch] = make_uint2(0u, 0u);
 }
 
 void launchRasterList(const void *args, void *stream)
@@ -291,7 +352,76 @@ int chooseTileShift(const swr_context *c, int renderTargets, size_t primitives)
     return (tiny && tiles64 / (c->world > 0 ? c->world : 1) >= 1024 && fits64()) ? 6 : 5;
 }
 
-// One draw = one or more passes of {geometry kernel, tile kernel}.
+// ---- cross-GPU barrier of a sort-first partition ---------------------------------------------------
+// Every rank owns kMaxRanks flag words in its arena header; word s is written by rank s only.  One warp: signal the
+// peers (release store of the epoch over NVLink), then wait until every peer's word has reached the epoch.
+// Stream order makes this a barrier between whole kernels: everything this rank enqueued before it -- e.g. the
+// geometry kernel's record pushes into the peers' scratch -- is visible at system scope before the signal, and
+// what follows (bin / tile kernels reading the own scratch) starts only after every peer has signalled.
+struct PeerFlags { uint32_t *flags[kMaxRanks]; };
+
+__global__ void peerBarrierKernel(PeerFlags pf, int rank, int world, uint32_t epoch, uint32_t *stickyFlag)
+{
+    const int lane = threadIdx.x;
+    __threadfence_system();
+    if (lane < world && lane != rank) {
+        uint32_t *dst = pf.flags[lane] + rank;
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(dst), "r"(epoch) : "memory");
+        const uint32_t *src = pf.flags[rank] + lane;
+        const long long t0 = clock64();
+        while (true) {
+            uint32_t v;
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
+            if ((int32_t)(v - epoch) >= 0) break;
+            if (clock64() - t0 > 6000000000ll) { atomicOr(stickyFlag, 8u); break; }     // ~3 s: a peer is gone; reported by swr_finish
+            __nanosleep(64);
+        }
+    }
+    __threadfence_system();
+}
+
+int enqueuePeerBarrier(swr_context *c)
+{
+    if (c->world <= 1) return 0;
+    if (!c->shardGeometry || !c->arena.ptr) return fail(-40, "no shared scratch / geometry shards set (swr_shared_scratch_create, swr_set_geometry_shards)");
+    PeerFlags pf;
+    for (int r = 0; r < kMaxRanks; ++r) pf.flags[r] = r < c->world ? reinterpret_cast<uint32_t *>(c->peerArena[r] + kArenaFlags) : nullptr;
+    Counters *ctr = reinterpret_cast<Counters *>(c->arena.ptr);
+    peerBarrierKernel<<<1, 32, 0, c->stream>>>(pf, c->rank, c->world, ++c->barrierEpoch, &ctr->stickyFlag);
+    c->stats.kernel_launches++;
+    CUDA_TRY(cudaGetLastError());
+    if (c->clearedKey) c->fencedSinceClear = true;
+    return 0;
+}
+
+__global__ void maxIndexKernel(const int32_t *idx, size_t n, int *out)
+{
+    int m = -1;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) m = max(m, idx[i]);
+    m = __reduce_max_sync(0xffffffffu, m);
+    if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
+
+// Largest index of a draw (host or device array): the extent of a host attribute array the reference API gives no size for.
+int maxIndexOf(swr_context *c, const int32_t *indices, size_t count, bool onDevice, int *out)
+{
+    if (!onDevice) {
+        int m = -1;
+        for (size_t i = 0; i < count; ++i) m = indices[i] > m ? indices[i] : m;
+        *out = m;
+        return 0;
+    }
+    if (int rc = c->maxIndexBuf.reserve(sizeof(int))) return rc;
+    const int init = -1;
+    CUDA_TRY(cudaMemcpyAsync(c->maxIndexBuf.ptr, &init, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    maxIndexKernel<<<148 * 4, 256, 0, c->stream>>>(indices, count, static_cast<int *>(c->maxIndexBuf.ptr));
+    c->stats.kernel_launches++;
+    CUDA_TRY(cudaMemcpyAsync(out, c->maxIndexBuf.ptr, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// One draw = one or more passes of {geometry kernel, [peer barrier,] bin kernel, tile kernel}.
 int drawCommon(swr_context *c, int drawMode, size_t count, const int32_t *indices, const void *rasterVerts, size_t rasterVertCount)
 {
     if (int rc = setDevice(c)) return rc;
@@ -317,12 +447,14 @@ int drawCommon(swr_context *c, int drawMode, size_t count, const int32_t *indice
         for (int i = 0; i < vs->attrib_count; ++i)
             if (!c->attribs[i].ptr) return fail(-8, "vertex attribute %d not set", i);
     }
+    const bool shard = c->shardGeometry && c->world > 1;
+    const bool pipeline = c->pipeline && !shard;             // (the peers write into ONE scratch set)
 
     // ---- streams: geometry-side work goes to the auxiliary stream.  Unless the caller opted into
     // overlapping whole draws, it first waits for everything already enqueued on the main stream
     // (so buffers the caller filled on that stream are visible to the vertex stage).
-    cudaStream_t gs = c->pipeline ? c->aux : c->stream;
-    if (c->pipeline && !c->overlapDraws) {
+    cudaStream_t gs = pipeline ? c->aux : c->stream;
+    if (pipeline && !c->overlapDraws) {
         CUDA_TRY(cudaEventRecord(c->evDrawStart, c->stream));
         CUDA_TRY(cudaStreamWaitEvent(gs, c->evDrawStart, 0));
     }
@@ -331,11 +463,12 @@ int drawCommon(swr_context *c, int drawMode, size_t count, const int32_t *indice
     GeomArgs g;
     memset(&g, 0, sizeof(g));
     const int32_t *devIndices = indices;
+    const bool idxOnDevice = isDevicePointer(indices);
     // Host indices of a big draw are streamed: the staging copies run on their own stream, attributes
     // first, then the indices pass by pass, and pass k's kernels only wait for their own slice -- the
     // PCIe transfer of pass k+1 runs under the kernels of pass k.
     const size_t idxBytes = nprims * per * sizeof(int32_t);
-    const bool streamIdx = !c->pipeline && !rasterVerts && !isDevicePointer(indices) && idxBytes >= ((size_t)32 << 20) &&
+    const bool streamIdx = !pipeline && !shard && !rasterVerts && !idxOnDevice && idxBytes >= ((size_t)32 << 20) &&
                            !getenv("SWR_NO_INDEX_STREAMING");
     cudaStream_t hs = gs;                                    // stream of the staging copies
     if (streamIdx) {
@@ -348,7 +481,7 @@ int drawCommon(swr_context *c, int drawMode, size_t count, const int32_t *indice
     DevBuf *stageAttrib = S ? c->stageAttribB : c->stageAttrib;
     bool staged = false;
     if (streamIdx && c->stageUsed[S]) CUDA_TRY(cudaStreamWaitEvent(hs, c->stageFree[S], 0));   // kernels of the draw that last read this set
-    if (!isDevicePointer(indices)) {
+    if (!idxOnDevice) {
         if (int rc = stageIdx.reserve(count * sizeof(int32_t))) return rc;
         if (!streamIdx) CUDA_TRY(cudaMemcpyAsync(stageIdx.ptr, indices, idxBytes, cudaMemcpyHostToDevice, gs));
         devIndices = static_cast<const int32_t *>(stageIdx.ptr);
@@ -365,13 +498,23 @@ int drawCommon(swr_context *c, int drawMode, size_t count, const int32_t *indice
         }
         g.rasterVerts = dv;
     } else {
+        int maxIndex = -2;                                   // computed at most once per draw
         for (int i = 0; i < vs->attrib_count; ++i) {
             const Attrib &a = c->attribs[i];
             const void *dp = a.ptr;
             if (!isDevicePointer(a.ptr)) {
-                if (a.bytes == 0) return fail(-9, "vertex attribute %d is host memory: its extent is required (bytes > 0)", i);
-                if (int rc = stageAttrib[i].reserve(a.bytes)) return rc;
-                CUDA_TRY(cudaMemcpyAsync(stageAttrib[i].ptr, a.ptr, a.bytes, cudaMemcpyHostToDevice, hs));
+                size_t bytes = a.bytes;
+                if (bytes == 0) {
+                    // The reference signature setVertexAttribPointer(index, stride, buffer) (VertexProcessor.h:88) carries no
+                    // extent: the vertices a draw can touch end at stride * (largest index + 1).
+                    if (a.stride <= 0) return fail(-9, "vertex attribute %d is host memory with stride %d: its extent is required (bytes > 0)", i, a.stride);
+                    if (maxIndex == -2)
+                        if (int rc = maxIndexOf(c, indices, nprims * per, idxOnDevice, &maxIndex)) return rc;
+                    if (maxIndex < 0) return fail(-9, "vertex attribute %d is host memory and the draw has no valid index", i);
+                    bytes = (size_t)a.stride * ((size_t)maxIndex + 1);
+                }
+                if (int rc = stageAttrib[i].reserve(bytes)) return rc;
+                CUDA_TRY(cudaMemcpyAsync(stageAttrib[i].ptr, a.ptr, bytes, cudaMemcpyHostToDevice, hs));
                 dp = stageAttrib[i].ptr;
                 staged = true;
             }
@@ -401,12 +544,13 @@ int drawCommon(swr_context *c, int drawMode, size_t count, const int32_t *indice
     const int paramStride = paramFloats(drawMode, nA, nP, useZ, useW);
     const bool needSpan = drawMode == SWR_DRAW_TRIANGLE && c->rasterMode != SWR_RASTER_BLOCK;
     const bool tri = drawMode == SWR_DRAW_TRIANGLE && !rasterVerts;
-    const size_t recBytes = sizeof(Box16) + 48 + (size_t)paramStride * 4 + (needSpan ? 48 : 0) + (c->debugStream ? 48 : 0);
+    const size_t recBytes = sizeof(Box16) + 48 + (size_t)paramStride * 4 + (needSpan ? 48 : 0);
     const size_t perPrimWorst = recBytes * (tri ? (size_t)(1 + kMaxFan - 1) : 1) + 16;
-    size_t passPrims = (c->scratchLimit / (c->pipeline ? 2 : 1)) / perPrimWorst;   // pipelining alternates two scratch sets
+    const size_t budget = shard ? (c->arena.bytes > kArenaHeader ? c->arena.bytes - kArenaHeader : 0) * 9 / 10 : c->scratchLimit / (pipeline ? 2 : 1);
+    size_t passPrims = budget / perPrimWorst;                           // pipelining alternates two scratch sets
     passPrims = std::max<size_t>(kBatch, passPrims / kBatch * kBatch);
     passPrims = std::min(passPrims, (nprims + kBatch - 1) / kBatch * kBatch);
-    if (c->pipeline) {
+    if (pipeline) {
         // big draws are cut into a few passes so that geometry(k+1) runs under tiles(k)
         int want = c->passesHint;
         if (want <= 0) {
@@ -425,40 +569,62 @@ int drawCommon(swr_context *c, int drawMode, size_t count, const int32_t *indice
         const size_t per_pass = ((nprims + want - 1) / want + kBatch - 1) / kBatch * kBatch;
         passPrims = std::min(passPrims, std::max<size_t>(kBatch, per_pass));
     }
-    const int tileShift = chooseTileShift(c, ps->render_targets, std::min(nprims, passPrims));   // density of ONE pass
+    // Tile ownership of a partition depends on the tile size, so with several ranks the size chosen for the first
+    // draw stays (every draw of a frame, and the composite, must agree on who owns which pixels).
+    int tileShift = c->world > 1 ? c->pinnedTileShift : 0;
+    if (tileShift == 0) {
+        tileShift = chooseTileShift(c, ps->render_targets, std::min(nprims, passPrims));   // density of ONE pass
+        if (c->world > 1) c->pinnedTileShift = tileShift;
+    } else if ((size_t)ps->render_targets * (1u << (2 * tileShift)) * 4 + 96 * 1024 > (size_t)227 * 1024) {
+        return fail(-2, "pixel shader '%s' stages %d render targets: the partition's %d-pixel tiles do not fit in shared memory (swr_set_tile_size(32) before the first draw)",
+                    ps->name, ps->render_targets, 1 << tileShift);
+    }
     const int T = 1 << tileShift;
     const int tilesX = (c->rtW + T - 1) / T, tilesY = (c->rtH + T - 1) / T;
     const size_t firstsCap = passPrims;                                  // multiple of kBatch
-    const size_t extrasCap = tri ? passPrims * (size_t)(kMaxFan - 1) : 0;
+    const size_t passBatches = passPrims / kBatch;
+    // fan extras: worst case 9 per primitive.  Sharded: every rank appends the extras of its own batches to its own
+    // share of the range (the cursor is local, no NVLink round trip), so the range is `world` worst-case shares.
+    size_t extraShare = 0, extrasCap = 0;
+    if (tri) {
+        if (shard) {
+            const size_t runs = (passBatches + kShardBatches - 1) / kShardBatches;
+            const size_t myBatchesMax = (runs + c->world - 1) / c->world * kShardBatches;
+            extraShare = myBatchesMax * kBatch * (size_t)(kMaxFan - 1);
+            extrasCap = extraShare * c->world;
+        } else {
+            extraShare = extrasCap = passPrims * (size_t)(kMaxFan - 1);
+        }
+    }
     const size_t recCap = firstsCap + extrasCap;
     if (recCap > 0xfffffff0u) return fail(-4, "pass too large");
-    const size_t passBatches = passPrims / kBatch;
     const int chunkWords = (int)((2 * passBatches + 31) / 32);
 
     // chunk + group binning as a pass of its own (bin.cuh); the per-tile list capacity is a tuning knob, tiles
     // beyond it bin themselves inside the tile kernel
     const bool binPass = !getenv("SWR_NO_BIN_PASS");
     const uint32_t groupCap = tileShift == 6 ? 2048u : 1024u;          // <= kGroupList of tile.cuh
-    for (ScratchSet &ss : c->sets) {
-        if (int rc = ss.bbox.reserve(recCap * sizeof(Box16))) return rc;
-        if (int rc = ss.gbox.reserve((recCap / kGroup + 1) * sizeof(Box16))) return rc;
-        if (int rc = ss.head.reserve(recCap * 48)) return rc;
-        if (int rc = ss.params.reserve(recCap * (size_t)paramStride * 4 + 16)) return rc;
-        if (needSpan) if (int rc = ss.span.reserve(recCap * 48)) return rc;
-        if (int rc = ss.tilemap.reserve((size_t)tilesX * tilesY * chunkWords * 4)) return rc;
-        if (int rc = ss.extra.reserve(passBatches * sizeof(uint2))) return rc;
-        if (binPass) {
-            if (int rc = ss.groupList.reserve((size_t)tilesX * tilesY * groupCap * 4)) return rc;
-            if (int rc = ss.groupCount.reserve((size_t)tilesX * tilesY * 4)) return rc;
+    const SetLayout L = layoutOf(recCap, paramStride, needSpan, (size_t)tilesX * tilesY, chunkWords, passBatches, groupCap, binPass);
+    if (shard) {
+        if (kArenaHeader + L.bytes > c->arena.bytes)
+            return fail(-41, "shared scratch of %zu bytes is too small for this draw (needs %zu)", c->arena.bytes, kArenaHeader + L.bytes);
+        ScratchSet &ss = c->sets[0];
+        ss.base = static_cast<char *>(c->arena.ptr) + kArenaHeader;
+        ss.ctr = reinterpret_cast<Counters *>(c->arena.ptr);
+        ss.countersInit = true;                                          // zeroed when the arena was created
+    } else {
+        for (ScratchSet &ss : c->sets) {
+            if (int rc = ss.blob.reserve(L.bytes)) return rc;
+            if (int rc = ss.counters.reserve(sizeof(Counters))) return rc;
+            ss.base = static_cast<char *>(ss.blob.ptr);
+            ss.ctr = static_cast<Counters *>(ss.counters.ptr);
+            if (!ss.countersInit) {
+                CUDA_TRY(cudaMemset(ss.counters.ptr, 0, sizeof(Counters)));
+                ss.countersInit = true;
+            }
+            if (!pipeline) break;                                        // without overlap only set 0 is used
         }
-        if (int rc = ss.counters.reserve(sizeof(Counters))) return rc;
-        if (!ss.countersInit) {
-            CUDA_TRY(cudaMemset(ss.counters.ptr, 0, sizeof(Counters)));
-            ss.countersInit = true;
-        }
-        if (!c->pipeline) break;                                         // without overlap only set 0 is used
     }
-    if (c->debugStream) if (int rc = c->dbgVerts.reserve(recCap * 48)) return rc;
     if (!c->hostFlags) {
         CUDA_TRY(cudaMallocHost((void **)&c->hostFlags, 64));
         c->hostFlags[0] = c->hostFlags[1] = 0;
@@ -474,10 +640,9 @@ int drawCommon(swr_context *c, int drawMode, size_t count, const int32_t *indice
     g.chunkWords = chunkWords;
     g.tileShift = tileShift;
     g.tilesX = tilesX; g.tilesY = tilesY;
-    g.extrasEnd = (uint32_t)recCap;
-    g.dbgVerts = c->debugStream ? static_cast<float *>(c->dbgVerts.ptr) : nullptr;
     g.rank = c->rank;
     g.world = c->world;
+    g.shard = shard && !rasterVerts ? 1 : 0;                  // raster lists: every rank walks the whole list
 
     TileArgs t;
     memset(&t, 0, sizeof(t));
@@ -501,7 +666,11 @@ int drawCommon(swr_context *c, int drawMode, size_t count, const int32_t *indice
 
     swr_launch_fn geomLaunch = rasterVerts ? &launchRasterList : vs->launch_geometry;
     swr_launch_fn tileLaunch = ps->launch_tiles[drawMode][tileShift - 5];
-    const uint32_t extrasBegin = (uint32_t)firstsCap;
+    // this rank's share of the extras range
+    const uint32_t extrasBegin = (uint32_t)(firstsCap + (g.shard ? extraShare * (size_t)c->rank : 0));
+    g.extrasEnd = (uint32_t)(extrasBegin + extraShare);
+    // what the scratch was cleared for: the bitmap's place and size (the peers rely on the clear, see below)
+    const uint64_t layoutKey = ((uint64_t)L.tilemap * 1000003ull) ^ ((uint64_t)tilesX * tilesY * (uint64_t)chunkWords * 2654435761ull) ^ ((uint64_t)extrasBegin << 1) | 1ull;
 
     if (streamIdx) {
         const size_t npass = (nprims + passPrims - 1) / passPrims;
@@ -521,29 +690,31 @@ int drawCommon(swr_context *c, int drawMode, size_t count, const int32_t *indice
     CUDA_TRY(cudaEventRecord(c->evGeom0, gs));
     bool firstPass = true;
     size_t passIndex = 0;
+    c->stats.last_geometry_ms = 0.0f;
     for (size_t first = 0; first < nprims; first += passPrims, ++passIndex) {
         const size_t n = std::min(passPrims, nprims - first);
         if (streamIdx) CUDA_TRY(cudaStreamWaitEvent(gs, c->idxReady[passIndex], 0));
-        ScratchSet &ss = c->sets[c->pipeline ? (c->passSeq & 1) : 0];
-        Counters *dc = static_cast<Counters *>(ss.counters.ptr);
+        ScratchSet &ss = c->sets[pipeline ? (c->passSeq & 1) : 0];
+        Counters *dc = ss.ctr;
         g.indices = devIndices + first * per;
         g.numPrims = (int)n;
         g.firstBatch = (uint32_t)(first / kBatch);
-        g.bbox = static_cast<Box16 *>(ss.bbox.ptr);
-        g.gbox = static_cast<Box16 *>(ss.gbox.ptr);
-        g.head = static_cast<float4 *>(ss.head.ptr);
-        g.params = static_cast<float *>(ss.params.ptr);
-        g.span = static_cast<float4 *>(ss.span.ptr);
-        g.tilemap = static_cast<uint32_t *>(ss.tilemap.ptr);
-        g.extra = static_cast<uint2 *>(ss.extra.ptr);
         g.extraAlloc = &dc->extraAlloc;
-        g.errorFlag = &dc->errorFlag;
-        t.bbox = g.bbox; t.gbox = g.gbox; t.head = g.head; t.params = g.params; t.span = g.span;
-        t.tilemap = g.tilemap;
-        t.groupList = binPass ? static_cast<uint32_t *>(ss.groupList.ptr) : nullptr;
-        t.groupCount = binPass ? static_cast<uint32_t *>(ss.groupCount.ptr) : nullptr;
+        for (int r = 0; r < kMaxRanks; ++r) memset(&g.sink[r], 0, sizeof(RecordSink));
+        const RecordSink own = sinkAt(ss.base, L, dc);
+        if (shard) {
+            for (int r = 0; r < c->world; ++r)
+                g.sink[r] = r == c->rank ? own : sinkAt(c->peerArena[r] + kArenaHeader, L, reinterpret_cast<Counters *>(c->peerArena[r]));
+        } else {
+            g.sink[c->rank] = own;
+        }
+        t.bbox = own.bbox; t.gbox = own.gbox; t.head = own.head; t.params = own.params; t.span = own.span;
+        t.tilemap = own.tilemap;
+        t.gcnt = own.gcnt;
+        t.groupList = binPass ? reinterpret_cast<uint32_t *>(ss.base + L.groupList) : nullptr;
+        t.groupCount = binPass ? reinterpret_cast<uint32_t *>(ss.base + L.groupCount) : nullptr;
         t.groupCap = groupCap;
-        t.extra = g.extra;
+        t.extra = own.extra;
         t.fragCounter = &dc->fragments;
         t.errorFlag = &dc->errorFlag;
         t.numPrims = (int)n;
@@ -551,10 +722,30 @@ int drawCommon(swr_context *c, int drawMode, size_t count, const int32_t *indice
 
         // geometry stream: wait until the tile kernel that last read this set is done, then refill it
         if (gs != c->stream && ss.tilePending) CUDA_TRY(cudaStreamWaitEvent(gs, ss.tileDone, 0));
-        CUDA_TRY(cudaMemsetAsync(ss.tilemap.ptr, 0, (size_t)tilesX * tilesY * chunkWords * 4, gs));
         const uint32_t init[2] = { extrasBegin, 0u };                    // extraAlloc, errorFlag
-        CUDA_TRY(cudaMemcpyAsync(&dc->extraAlloc, init, sizeof(init), cudaMemcpyHostToDevice, gs));
-        if (c->debugStream) CUDA_TRY(cudaMemsetAsync(c->dbgVerts.ptr, 0xff, recCap * 48, gs));
+        auto clearSet = [&]() -> int {
+            CUDA_TRY(cudaMemsetAsync(own.tilemap, 0, (size_t)tilesX * tilesY * chunkWords * 4, gs));
+            CUDA_TRY(cudaMemcpyAsync(&dc->extraAlloc, init, sizeof(init), cudaMemcpyHostToDevice, gs));
+            return 0;
+        };
+        if (shard) {
+            // The peers' geometry kernels write into this rank's bitmap and records, so (1) the bitmap must be clear
+            // and the previous pass's tile kernel done on EVERY rank before any geometry kernel of this pass starts,
+            // and (2) every geometry kernel must be done before any tile kernel reads.  (1) is a clear followed by a
+            // barrier; the clear is issued right after the tile kernel of the previous pass, so that a barrier the
+            // host enqueues anyway at the end of a frame (swr_peer_barrier) also serves as (1) of the next draw.
+            if (c->clearedKey != layoutKey) {
+                if (int rc = clearSet()) return rc;
+                c->clearedKey = layoutKey;
+                c->fencedSinceClear = false;
+            }
+            if (!c->fencedSinceClear)
+                if (int rc = enqueuePeerBarrier(c)) return rc;
+            c->clearedKey = 0;                                           // the geometry kernels are about to dirty it
+            c->fencedSinceClear = false;
+        } else {
+            if (int rc = clearSet()) return rc;
+        }
         geomLaunch(&g, gs);
         if (first + passPrims >= nprims) CUDA_TRY(cudaEventRecord(c->evGeom1, gs));
         // main stream: tiles of this pass after its geometry
@@ -562,6 +753,8 @@ int drawCommon(swr_context *c, int drawMode, size_t count, const int32_t *indice
             CUDA_TRY(cudaEventRecord(ss.geomDone, gs));
             CUDA_TRY(cudaStreamWaitEvent(c->stream, ss.geomDone, 0));
         }
+        if (shard)
+            if (int rc = enqueuePeerBarrier(c)) return rc;               // (2)
         if (firstPass) CUDA_TRY(cudaEventRecord(c->evTile0, c->stream));
         firstPass = false;
         if (binPass) {
@@ -573,11 +766,13 @@ int drawCommon(swr_context *c, int drawMode, size_t count, const int32_t *indice
             CUDA_TRY(cudaEventRecord(ss.tileDone, c->stream));
             ss.tilePending = true;
         }
+        if (shard) {
+            if (int rc = clearSet()) return rc;                          // ready for the next pass / draw of the same shape
+            c->clearedKey = layoutKey;
+            c->fencedSinceClear = false;
+        }
         c->stats.kernel_launches += 2;
         c->stats.passes++;
-        c->lastPassPrims = (int)n;
-        c->lastFirstBatch = g.firstBatch;
-        c->lastSet = (int)(&ss - c->sets);
         c->passSeq++;
     }
     CUDA_TRY(cudaEventRecord(c->evTile1, c->stream));
@@ -588,7 +783,6 @@ int drawCommon(swr_context *c, int drawMode, size_t count, const int32_t *indice
     CUDA_TRY(cudaGetLastError());
     c->haveDrawEvents = true;
     c->lastDrawMode = drawMode;
-    c->lastExtrasBegin = extrasBegin;
     c->stats.last_tile_size = T;
     return 0;
 }
@@ -643,7 +837,7 @@ void swr_destroy(swr_context *c)
     cudaSetDevice(c->device);
     if (c->aux) cudaStreamSynchronize(c->aux);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    DevBuf *bufs[] = { &c->dbgVerts, &c->stageIdx, &c->stageIdxB, &c->l2flush, &c->ownedIdx, &c->tileStats };
+    DevBuf *bufs[] = { &c->stageIdx, &c->stageIdxB, &c->l2flush, &c->ownedIdx, &c->tileStats, &c->arena, &c->soVerts, &c->soIndices, &c->soCounts, &c->maxIndexBuf };
     for (DevBuf *b : bufs) b->release();
     for (int i = 0; i < SWR_MAX_VERTEX_ATTRIBS; ++i) c->stageAttribB[i].release();
     for (ScratchSet &ss : c->sets) ss.release();
@@ -759,6 +953,7 @@ int swr_set_tile_size(swr_context *c, int tile_size)
 {
     if (!c) return fail(-1, "null context");
     if (tile_size != 0 && tile_size != 32 && tile_size != 64) return fail(-2, "tile size must be 0, 32 or 64");
+    if (tile_size != c->tileSizeReq) c->pinnedTileShift = 0;
     c->tileSizeReq = tile_size;
     return 0;
 }
@@ -767,9 +962,67 @@ int swr_set_tile_partition(swr_context *c, int rank, int world)
 {
     if (!c) return fail(-1, "null context");
     if (world < 1 || rank < 0 || rank >= world) return fail(-2, "bad partition %d/%d", rank, world);
+    if (rank != c->rank || world != c->world) c->pinnedTileShift = 0;
     c->rank = rank;
     c->world = world;
+    if (world == 1) c->shardGeometry = false;
     return 0;
+}
+
+int swr_shared_scratch_create(swr_context *c, size_t bytes, void **base)
+{
+    if (!c || !base) return fail(-1, "null argument");
+    if (int rc = setDevice(c)) return rc;
+    if (bytes < kArenaHeader + ((size_t)1 << 20)) return fail(-2, "shared scratch must be at least %zu bytes", kArenaHeader + ((size_t)1 << 20));
+    CUDA_TRY(cudaStreamSynchronize(c->aux));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->arena.release();
+    c->shardGeometry = false;
+    c->sets[0].release();
+    c->sets[1].release();
+    c->arena.bytes = 0;
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);                   // exact size: the peers compute the same layout from it
+    if (e != cudaSuccess) return fail(-101, "cudaMalloc(%zu bytes) for the shared scratch: %s", bytes, cudaGetErrorString(e));
+    c->arena.ptr = p;
+    c->arena.bytes = bytes;
+    CUDA_TRY(cudaMemset(p, 0, kArenaHeader));
+    c->barrierEpoch = 0;
+    c->clearedKey = 0;
+    c->fencedSinceClear = false;
+    *base = p;
+    return 0;
+}
+
+int swr_set_geometry_shards(swr_context *c, int rank, int world, void *const *arenas)
+{
+    if (!c) return fail(-1, "null context");
+    if (int rc = setDevice(c)) return rc;
+    if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world) return fail(-2, "bad partition %d/%d (at most %d ranks)", rank, world, kMaxRanks);
+    CUDA_TRY(cudaStreamSynchronize(c->aux));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (world > 1) {
+        if (!arenas) return fail(-1, "null arena list");
+        if (!c->arena.ptr) return fail(-40, "swr_shared_scratch_create first");
+        for (int r = 0; r < world; ++r) {
+            if (r != rank && !arenas[r]) return fail(-2, "shared scratch of rank %d is null", r);
+            c->peerArena[r] = r == rank ? static_cast<char *>(c->arena.ptr) : static_cast<char *>(arenas[r]);
+        }
+    }
+    if (rank != c->rank || world != c->world) c->pinnedTileShift = 0;
+    c->rank = rank;
+    c->world = world;
+    c->shardGeometry = world > 1;
+    c->clearedKey = 0;
+    c->fencedSinceClear = false;
+    return 0;
+}
+
+int swr_peer_barrier(swr_context *c)
+{
+    if (!c) return fail(-1, "null context");
+    if (int rc = setDevice(c)) return rc;
+    return enqueuePeerBarrier(c);
 }
 
 int swr_set_stream(swr_context *c, void *cuda_stream)
@@ -826,7 +1079,7 @@ int swr_finish(swr_context *c)
     for (int k = 0; k < 2; ++k) {
         ScratchSet &ss = c->sets[k];
         if (!ss.countersInit) continue;
-        Counters *dc = static_cast<Counters *>(ss.counters.ptr);
+        Counters *dc = ss.ctr;
         CUDA_TRY(cudaMemcpyAsync(c->hostFlags + k, &dc->stickyFlag, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(cudaMemsetAsync(&dc->stickyFlag, 0, sizeof(uint32_t), c->stream));
     }
@@ -837,6 +1090,8 @@ int swr_finish(swr_context *c)
         c->hostFlags[0] = c->hostFlags[1] = 0;
         if (f & 1u) return fail(-30, "geometry scratch exhausted: the last draw produced nothing (raise swr_set_scratch_limit)");
         if (f & 2u) return fail(-31, "a line longer than %d DDA steps was dropped", kMaxLineSteps);
+        if (f & 4u) return fail(-32, "a clipped polygon of more than %d vertices was dropped", kMaxPoly);
+        if (f & 8u) return fail(-33, "peer barrier timed out: a rank of the partition did not reach it");
     }
     return 0;
 }
@@ -851,7 +1106,7 @@ int swr_get_stats(swr_context *c, swr_stats *out)
     for (ScratchSet &ss : c->sets)
         if (ss.countersInit) {
             Counters h;
-            CUDA_TRY(cudaMemcpy(&h, ss.counters.ptr, sizeof(h), cudaMemcpyDeviceToHost));
+            CUDA_TRY(cudaMemcpy(&h, ss.ctr, sizeof(h), cudaMemcpyDeviceToHost));
             c->stats.fragments += h.fragments;
         }
     if (c->haveDrawEvents) {
@@ -872,7 +1127,7 @@ int swr_reset_stats(swr_context *c)
     CUDA_TRY(cudaStreamSynchronize(c->aux));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     for (ScratchSet &ss : c->sets)
-        if (ss.countersInit) CUDA_TRY(cudaMemset(&static_cast<Counters *>(ss.counters.ptr)->fragments, 0, sizeof(unsigned long long)));
+        if (ss.countersInit) CUDA_TRY(cudaMemset(&ss.ctr->fragments, 0, sizeof(unsigned long long)));
     const uint64_t scratch = c->stats.scratch_bytes;
     const int tile = c->stats.last_tile_size;
     memset(&c->stats, 0, sizeof(c->stats));
@@ -1123,53 +1378,6 @@ int64_t swr_debug_read_tile_stats(swr_context *c, uint32_t *out, int64_t cap_til
     const int64_t n = std::min<int64_t>(cap_tiles, c->lastTiles);
     if (cudaMemcpy(out, c->tileStats.ptr, (size_t)n * 64, cudaMemcpyDeviceToHost) != cudaSuccess) return fail(-100, "copy failed");
     return c->lastTiles;
-}
-
-int swr_debug_enable_stream(swr_context *c, int enable)
-{
-    if (!c) return fail(-1, "null context");
-    c->debugStream = enable != 0;
-    return 0;
-}
-
-// Records of the last pass in emission order (per batch: original slots, then fan extras).
-int64_t swr_debug_read_stream(swr_context *c, int16_t *bbox, uint32_t *ordinal, float *verts, int64_t cap)
-{
-    if (!c) return fail(-1, "null context");
-    if (int rc = setDevice(c)) return rc;
-    if (cudaStreamSynchronize(c->stream) != cudaSuccess) return fail(-100, "sync failed");
-    const int n = c->lastPassPrims;
-    const ScratchSet &ls = c->sets[c->lastSet];
-    cudaStreamSynchronize(c->aux);
-    if (n == 0 || !ls.bbox.ptr) return 0;
-    const int batches = (n + kBatch - 1) / kBatch;
-    std::vector<uint2> extra(batches);
-    if (cudaMemcpy(extra.data(), ls.extra.ptr, sizeof(uint2) * batches, cudaMemcpyDeviceToHost) != cudaSuccess) return fail(-100, "copy failed");
-    size_t maxRec = (size_t)batches * kBatch;
-    for (const uint2 &e : extra) maxRec = std::max(maxRec, (size_t)e.x + e.y);
-    std::vector<Box16> hb(maxRec);
-    std::vector<float> hv;
-    if (cudaMemcpy(hb.data(), ls.bbox.ptr, sizeof(Box16) * maxRec, cudaMemcpyDeviceToHost) != cudaSuccess) return fail(-100, "copy failed");
-    if (verts && c->dbgVerts.ptr) {
-        hv.resize(maxRec * 12);
-        if (cudaMemcpy(hv.data(), c->dbgVerts.ptr, sizeof(float) * 12 * maxRec, cudaMemcpyDeviceToHost) != cudaSuccess) return fail(-100, "copy failed");
-    }
-    int64_t out = 0;
-    auto put = [&](size_t rec, uint32_t ord) {
-        if (out < cap) {
-            if (bbox) memcpy(bbox + out * 4, &hb[rec], 8);
-            if (ordinal) ordinal[out] = ord;
-            if (verts && !hv.empty()) memcpy(verts + out * 12, &hv[rec * 12], 48);
-        }
-        ++out;
-    };
-    for (int b = 0; b < batches; ++b) {
-        const int cnt = std::min(kBatch, n - b * kBatch);
-        const uint32_t ord0 = (c->lastFirstBatch + (uint32_t)b) * SWR_ORDINAL_STRIDE;
-        for (int s = 0; s < cnt; ++s) put((size_t)b * kBatch + s, ord0 + (uint32_t)s);
-        for (uint32_t e = 0; e < extra[b].y; ++e) put((size_t)extra[b].x + e, ord0 + (uint32_t)cnt + e);
-    }
-    return out;
 }
 
 } // extern "C"

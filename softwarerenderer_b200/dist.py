@@ -152,6 +152,59 @@ class TileMirror:
         self.peers = []
 
 
+class GeometryShards:
+    """Sharded vertex stage of a sort-first partition (swr_set_geometry_shards): every rank runs 1/world of the batches
+    and its geometry kernel stores each surviving record straight into the scratch of the ranks whose tiles it touches
+    (peer mappings over NVLink); the kernels of the ranks are ordered by the library's own flag barrier.
+    torch.distributed only carries the 64-byte IPC handles at set-up.  All ranks must pass the same `scratch_bytes`
+    and then issue the same sequence of draws and barrier() calls."""
+
+    def __init__(self, rasterizer, rank: int, world: int, device, scratch_bytes: int):
+        import torch
+        import torch.distributed as dist
+        from . import api
+        self.r, self.rank, self.world = rasterizer, rank, world
+        self.peers = []
+        base = rasterizer.createSharedScratch(scratch_bytes)
+        try:
+            mine = api.ipc_handle(base)
+        except Exception as e:
+            mine = ("error", str(e))
+        handles = [None] * world
+        dist.all_gather_object(handles, mine)
+        bad = [h for h in handles if h[0] == "error"]
+        if bad:
+            raise RuntimeError(f"GeometryShards: a scratch arena cannot be exported over CUDA IPC: {bad[0][1]}")
+        arenas, err = [0] * world, None
+        try:
+            for i, (h, off) in enumerate(handles):
+                if i != rank:
+                    arenas[i] = rasterizer.ipcOpen(h, off)
+                    self.peers.append(arenas[i])
+        except Exception as e:
+            err = e
+        ok = torch.tensor([0 if err else 1], dtype=torch.int32, device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)          # also the barrier "every arena exists and is zeroed"
+        if int(ok.item()) == 0:
+            for p in self.peers:
+                rasterizer.ipcClose(p)
+            self.peers = []
+            raise RuntimeError(f"GeometryShards: a peer scratch arena cannot be mapped: {err}")
+        rasterizer.setGeometryShards(rank, world, arenas)
+
+    def barrier(self) -> None:
+        self.r.peerBarrier()
+
+    def run(self, slot: int) -> None:       # same call shape as TileComposite.run / TileMirror.run
+        self.r.peerBarrier()
+
+    def close(self) -> None:
+        self.r.setGeometryShards(0, 1, [])
+        for p in self.peers:
+            self.r.ipcClose(p)
+        self.peers = []
+
+
 class ReplicatedUpload:
     """Host -> every GPU, for buffers that all ranks need in full (sort-first replicates the geometry): each rank
     copies only 1/world of the bytes over its own PCIe link, then one NCCL all-gather over NVLink gives every

@@ -168,7 +168,7 @@ int run(swr_scene *s)
     g.nA = TR::NA; g.nP = TR::NP; g.useZ = TR::Z; g.useW = TR::W;
     g.paramStride = paramFloats(s->draw_mode, g.nA, g.nP, g.useZ, g.useW);
     uint32_t errorFlags[2] = { 0, 0 };
-    g.errorFlag = errorFlags;
+    g.world = 1;
     g.noTightBox = getenv("HOSTCHECK_NO_TIGHT_BOX") ? 1 : 0;
 
     const size_t cap = (size_t)nprim * (s->draw_mode == 2 ? kMaxFan : 1) + 1;
@@ -177,7 +177,9 @@ int run(swr_scene *s)
     st.head.resize(cap * 3);
     st.span.resize(cap * 3);
     st.params.resize(cap * (size_t)g.paramStride + 4);
-    g.bbox = st.bbox.data(); g.head = st.head.data(); g.span = st.span.data(); g.params = st.params.data();
+    RecordSink &sink = g.sink[0];
+    sink.bbox = st.bbox.data(); sink.head = st.head.data(); sink.span = st.span.data(); sink.params = st.params.data();
+    sink.errorFlag = errorFlags;
 
     // ---- geometry stage, in emission order: per batch the original slots, then the fan extras
     uint32_t nextRec = 0;
@@ -198,23 +200,23 @@ int run(swr_scene *s)
                 int n = 3;
                 if (mask) n = clipTriangle<NA, NP>(a, b, mask, &poly);
                 if (n >= 3) {
-                    box = emitClipTriangle<NA, NP>(g, rec, ord0 + (uint32_t)i, poly[0], poly[1], poly[2]);
+                    box = emitClipTriangle<NA, NP>(g, sink, rec, ord0 + (uint32_t)i, poly[0], poly[1], poly[2]);
                     for (int k = 1; k + 2 < n; ++k) {
                         const uint32_t er = nextRec++;
-                        st.bbox[er] = emitClipTriangle<NA, NP>(g, er, ord0 + slotExtra++, poly[0], poly[k + 1], poly[k + 2]);
+                        st.bbox[er] = emitClipTriangle<NA, NP>(g, sink, er, ord0 + slotExtra++, poly[0], poly[k + 1], poly[k + 2]);
                         extras.push_back(er);
                     }
                 }
             } else if (s->draw_mode == 1) {
                 V c0, c1;
                 shadeHost<VS>(s, ip[0], c0); shadeHost<VS>(s, ip[1], c1);
-                box = emitClipLine<NA, NP>(g, rec, ord0 + (uint32_t)i, c0, c1);
+                box = emitClipLine<NA, NP>(g, sink, rec, ord0 + (uint32_t)i, c0, c1);
             } else {
                 V c0;
                 shadeHost<VS>(s, ip[0], c0);
                 if (outcode(c0.x, c0.y, c0.z, c0.w) == 0) {
                     toScreen(g, c0);
-                    box = emitScreenPoint<NA, NP>(g, rec, ord0 + (uint32_t)i, c0);
+                    box = emitScreenPoint<NA, NP>(g, sink, rec, ord0 + (uint32_t)i, c0);
                 }
             }
             st.bbox[rec] = box;
@@ -226,7 +228,7 @@ int run(swr_scene *s)
     // ---- raster stage: every record in emission order, every 8x8 block of its footprint
     TileArgs t;
     memset(&t, 0, sizeof(t));
-    t.bbox = g.bbox; t.head = g.head; t.params = g.params; t.span = g.span; t.paramStride = g.paramStride;
+    t.bbox = sink.bbox; t.head = sink.head; t.params = sink.params; t.span = sink.span; t.paramStride = g.paramStride;
     t.rtWidth = s->width; t.rtHeight = s->height;
     t.scMinX = g.scMinX; t.scMinY = g.scMinY; t.scMaxX = g.scMaxX; t.scMaxY = g.scMaxY;
     PixelData p;
@@ -347,11 +349,12 @@ extern "C" long hostcheck_tight_box_fuzz(int kind, long n, unsigned long long se
     g.nA = 0; g.nP = 0; g.useZ = 0; g.useW = 0;
     g.paramStride = 4;
     uint32_t errorFlags[2] = { 0, 0 };
-    g.errorFlag = errorFlags;
+    g.world = 1;
     std::vector<float4> head(6);
     std::vector<float> params(16);
     std::vector<float4> span(6);
-    g.head = head.data(); g.params = params.data(); g.span = span.data();
+    RecordSink &sink = g.sink[0];
+    sink.head = head.data(); sink.params = params.data(); sink.span = span.data(); sink.errorFlag = errorFlags;
     long bad = 0;
     *checked = 0; *tightened = 0;
     for (long it = 0; it < n; ++it) {
@@ -374,9 +377,9 @@ extern "C" long hostcheck_tight_box_fuzz(int kind, long n, unsigned long long se
             v[k].x = (float)x; v[k].y = (float)y; v[k].z = 0.5f; v[k].w = 1.0f;
         }
         g.noTightBox = 0;
-        const Box16 tight = emitScreenTriangle<3, 0>(g, 0, 0, true, v[0], v[1], v[2]);
+        const Box16 tight = emitScreenTriangle<3, 0>(g, sink, 0, 0, true, v[0], v[1], v[2]);
         g.noTightBox = 1;
-        const Box16 ref = emitScreenTriangle<3, 0>(g, 1, 0, true, v[0], v[1], v[2]);
+        const Box16 ref = emitScreenTriangle<3, 0>(g, sink, 1, 0, true, v[0], v[1], v[2]);
         if (ref.x0 > ref.x1) { if (tight.x0 <= tight.x1) ++bad; continue; }
         ++*checked;
         const float4 h0 = head[3], h1 = head[4], h2 = head[5];

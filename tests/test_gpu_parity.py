@@ -333,3 +333,60 @@ def test_rasterizer_draw_triangle_list(oracle, renderers, name, mode, frags):
     sr.r.drawTriangleList(verts, idx)
     sr.r.finish()
     assert int(sr.r.stats().fragments) == frags
+
+
+@pytest.mark.parametrize("name", ["c0_block", "c3_small", "heavy_clip", "lines", "c2_depth"])
+def test_sharded_geometry_two_ranks_on_one_gpu(oracle, name):
+    """swr_set_geometry_shards: two ranks (here two contexts on one GPU that see each other's scratch directly) each
+    run half of the batches and push every record into the scratch of the rank that owns its tiles; the ranks'
+    kernels are ordered by the library's flag barrier.  The union of the two framebuffers is the reference's frame,
+    bit for bit, including the per-pixel draw order (prim_id = last writer's emission ordinal)."""
+    from softwarerenderer_b200.api import SceneRenderer
+    scene = {
+        "c0_block": lambda: S.config_c0(ntri=40000, ps=S.PS_COUNT_ID, raster_mode=S.RASTER_BLOCK),
+        "c3_small": lambda: S.config_c3(700, 500, 960, 540, ps=S.PS_COUNT_ID),
+        "heavy_clip": lambda: S.config_c0(ps=S.PS_COUNT_ID, ntri=20000).replace(vs=S.VS_MVP_COLOR, mvp=common.heavy_clip_mvp(), raster_mode=S.RASTER_SPAN),
+        "lines": lambda: S.config_c4(200, 100, 960, 540),
+        "c2_depth": lambda: S.config_c2(300, 200, 960, 540),
+    }[name]()
+    want = oracle.run(scene, "oracle")
+    world = 2
+    srs = [SceneRenderer(scene.width, scene.height) for _ in range(world)]
+    for sr in srs:
+        sr.draw(scene)           # one ordinary draw first: every staging buffer exists afterwards (a cudaMalloc inside the
+                                 # second context's draw would wait for the first context's barrier kernel -- one GPU here)
+    arenas = [sr.r.createSharedScratch(768 << 20) for sr in srs]
+    for rank, sr in enumerate(srs):
+        sr.r.setGeometryShards(rank, world, arenas)
+        sr.targets.clear()
+        sr.r.resetStats()
+    for sr in srs:
+        sr.r.finish()
+    for rep in range(2):                                     # twice: the scratch is reused, the barrier epochs advance
+        for sr in srs:
+            sr.targets.clear()
+            sr.r.resetStats()
+        for sr in srs:
+            sr.r.finish()
+        for sr in srs:
+            sr.draw(scene, wait=False)                        # both ranks enqueue; the barrier kernels meet on the device
+        for sr in srs:
+            sr.r.peerBarrier()
+        outs = []
+        for sr in srs:
+            sr.r.finish()
+            outs.append(sr.targets.download())
+        frags = sum(int(sr.r.stats().fragments) for sr in srs)
+        assert frags == want["fragments"], (name, rep)
+        acc = {k: outs[0][k].copy() for k in common.BUFFERS}
+        touched = outs[1]["count"] > 0 if scene.ps in (S.PS_COUNT_ID, S.PS_VARY_DUMP) else outs[1]["color"] != 0
+        if scene.ps == S.PS_COUNT_ID:
+            assert not np.any(touched & (acc["count"] > 0)), "two ranks rendered the same pixel"
+        for k in ("count", "prim_id", "color", "depth"):
+            acc[k][touched] = outs[1][k][touched]
+        keys = ("count", "prim_id") if scene.ps == S.PS_COUNT_ID else ("color", "depth") if scene.ps == S.PS_GOURAUD_DEPTH else ("color",)
+        assert not common.diff_buffers(acc, want, keys), (name, rep)
+    for sr in srs:
+        sr.r.setGeometryShards(0, 1, [])
+    for sr in srs:
+        sr.close()

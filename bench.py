@@ -196,7 +196,7 @@ def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
     from softwarerenderer_b200 import api
-    from softwarerenderer_b200.dist import ReplicatedUpload, TileComposite, TileMirror
+    from softwarerenderer_b200.dist import GeometryShards, ReplicatedUpload, TileComposite, TileMirror
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -251,8 +251,17 @@ def run_gpu_arm(args):
         u.tex_h, u.tex_w = scene.texture.shape
     r.setUniforms(u)
     r.setTilePartition(rank, world)
+    shards = None
+    if world > 1 and args.geometry == "sharded":
+        # sharded vertex stage: every rank runs 1/world of the batches and pushes the records to the tile owners
+        try:
+            shards = GeometryShards(r, rank, world, dev, int(args.scratch_gb * (1 << 30)))
+        except RuntimeError as e:                     # raised on every rank together
+            print(f"[bench] {e}; geometry stays replicated", file=sys.stderr)
+            args.geometry = "replicated"
 
     count = int(scene.indices.size)
+    count_all = count
 
     def step_resident():
         v.setVertexAttribPointer(0, scene.stride, d_vert)
@@ -267,7 +276,20 @@ def run_gpu_arm(args):
     if world > 1:
         up_group = dist.new_group(ranks=list(range(world)))
         up_stream = torch.cuda.Stream(device=dev)
-        repl = [ReplicatedUpload([scene.vertices, scene.indices], rank, world, dev, group=up_group) for _ in range(2)]
+        if shards is not None:
+            # the vertices are needed in full by every rank (replicated: 1/world over PCIe each + one all-gather over
+            # NVLink); of the indices a rank only reads the runs of 16 batches it processes: they go straight from its
+            # own host memory to their place in the index buffer
+            run_len = 16 * 1024 * (scene.draw_mode + 1)
+            n_runs = -(-count_all // run_len)
+            pad_runs = -(-n_runs // world) * world
+            h_pad = np.zeros(pad_runs * run_len, dtype=np.int32)
+            h_pad[:count_all] = scene.indices
+            own_runs = torch.from_numpy(h_pad.reshape(pad_runs // world, world, run_len)[:, rank].copy()).pin_memory()
+            d_idx_sh = [torch.zeros(pad_runs * run_len, dtype=torch.int32, device=dev) for _ in range(2)]
+            repl = [ReplicatedUpload([scene.vertices], rank, world, dev, group=up_group) for _ in range(2)]
+        else:
+            repl = [ReplicatedUpload([scene.vertices, scene.indices], rank, world, dev, group=up_group) for _ in range(2)]
         up_ready = [torch.cuda.Event(), torch.cuda.Event()]
         up_free = [torch.cuda.Event(), torch.cuda.Event()]
         up_state = {"k": 0, "ptrs": [None, None], "drawn": [False, False]}
@@ -276,7 +298,11 @@ def run_gpu_arm(args):
             with torch.cuda.stream(up_stream):
                 if up_state["drawn"][slot]:
                     up_stream.wait_event(up_free[slot])          # the draw that last read this buffer is done
-                up_state["ptrs"][slot] = repl[slot].run()
+                ptrs = repl[slot].run()
+                if shards is not None:
+                    d_idx_sh[slot].view(-1, world, run_len)[:, rank].copy_(own_runs, non_blocking=True)
+                    ptrs = [ptrs[0], d_idx_sh[slot].data_ptr()]
+                up_state["ptrs"][slot] = ptrs
                 up_ready[slot].record(up_stream)
 
     def step_e2e():
@@ -332,7 +358,8 @@ def run_gpu_arm(args):
             # fused composite: the tile kernel stores finished tiles into the peers' surfaces (CUDA IPC / NVLink);
             # per step only a one-word NCCL all-reduce remains, as the barrier
             try:
-                comp = TileMirror(r, api.RT_COLOR, targets[api.RT_COLOR].data_ptr(), rank, world, dev)
+                comp = TileMirror(r, api.RT_COLOR, targets[api.RT_COLOR].data_ptr(), rank, world, dev,
+                                  peer_barrier=shards.barrier if shards is not None else None)
                 clear()
                 comp.barrier()
             except RuntimeError as e:                 # raised on every rank together (see TileMirror)
@@ -410,7 +437,7 @@ def run_gpu_arm(args):
             "dtype": "f32", "data": "synthetic",
             "triangles_per_s": scene.num_primitives / (ms_step * 1e-3),
             "fragments_per_step": fragments, "triangles_per_step": scene.num_primitives,
-            "config": {"workload": wl, "tile_size": tile, "parallelism": (f"sort-first tiles x{world}, composite: " + ("tile kernel stores to peer surfaces over NVLink + 1-word NCCL barrier" if args.composite == "mirror" else "pack + NCCL all-gather + unpack")) if world > 1 else "single GPU",
+            "config": {"workload": wl, "tile_size": tile, "parallelism": (f"sort-first tiles x{world}; geometry " + ("sharded by batches, records pushed to the tile owners over NVLink, flag barrier between the GPUs" if shards is not None else "replicated") + "; composite: " + ("tile kernel stores to peer surfaces over NVLink + " + ("flag barrier" if shards is not None else "1-word NCCL barrier") if args.composite == "mirror" else "pack + NCCL all-gather + unpack")) if world > 1 else "single GPU",
                        "l2": "inputs larger than L2: 240 MB of indices + vertices are re-read every step (126 MB L2)"
                              if scene.indices.nbytes + scene.vertices.nbytes > 126e6 else "inputs fit in L2 (no flush between steps)",
                        "clear": "render targets cleared once before timing (the Gouraud shader overwrites)"},
@@ -422,10 +449,11 @@ def run_gpu_arm(args):
                          "draw": {"algorithmic_bytes": geom_b + frag_b / world, "achieved": ach_draw, "frac": ach_draw / peak,
                                   "distinct_vertices": v_ref}},
             "e2e": {"value": fragments / (ms_e2e / args.steps * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
-                    "h2d_bytes_per_step": int(scene.vertices.nbytes + scene.indices.nbytes) if world == 1 else int(repl[0].h2d_bytes * world),
+                    "h2d_bytes_per_step": int(scene.vertices.nbytes + scene.indices.nbytes) if world == 1 else int((repl[0].h2d_bytes + (own_runs.numel() * 4 if shards is not None else 0)) * world),
                     "d2h_bytes_per_step": int(W * H * 4),
                     "path": "host buffers -> swr_draw_elements (staged by the library, indices streamed pass by pass) -> frame to host" if world == 1 else
-                            f"each rank uploads 1/{world} of the geometry, NCCL all-gather replicates it, draw + composite, rank 0 reads the frame"},
+                            (f"each rank uploads 1/{world} of the vertices (NCCL all-gather replicates them) and the index runs of its own batches, draw + composite, rank 0 reads the frame"
+                             if shards is not None else f"each rank uploads 1/{world} of the geometry, NCCL all-gather replicates it, draw + composite, rank 0 reads the frame")},
             "gpu_launches": launches_total,
             "clocks": clocks,
         }
@@ -449,9 +477,14 @@ def main():
     ap.add_argument("--composite", default="mirror", choices=["mirror", "nccl"],
                     help="N>1: fused peer stores from the tile kernel (default) or pack + NCCL all-gather + unpack")
     ap.add_argument("--tile", type=int, default=0)
+    ap.add_argument("--geometry", default="sharded", choices=["sharded", "replicated"],
+                    help="N>1: vertex stage sharded by batches with records pushed to the tile owners (default) or run in full by every rank")
+    ap.add_argument("--scratch-gb", type=float, default=0.0, help="N>1, sharded geometry: size of the shared scratch arena per rank (0 = by workload)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.scratch_gb <= 0:
+        args.scratch_gb = 40.0 if args.workload == "c5" else 14.0
     if args.impl == "reference":
         run_reference_arm(args)
     else:

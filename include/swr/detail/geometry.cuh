@@ -424,7 +424,7 @@ SWR_HD Box16 setupScreenTriangle(const GeomArgs &g, uint32_t ordinal, bool doCul
 // Write a set-up triangle as record `rec` of `sink`: head, planes in the order z?, invw?, avar[nA], pvar[nP]
 // (one float4 (a, b, c, 0) each), span halves.
 template <int NA, int NP>
-SWR_HD void storeTriangle(const GeomArgs &g, const RecordSink &sink, uint32_t rec, const TriRecord<NA, NP> &R)
+SWR_HD void storeTriangle(const GeomArgs &g, const RecordSink &sink, uint32_t rec, const TriRecord<NA, NP> &R, float4 *spanDst = nullptr)
 {
     float4 *hd = sink.head + (size_t)rec * 3;
     hd[0] = R.h0; hd[1] = R.h1; hd[2] = R.h2;
@@ -438,7 +438,7 @@ SWR_HD void storeTriangle(const GeomArgs &g, const RecordSink &sink, uint32_t re
     for (int i = 0; i < NP; ++i)
         if (i < g.nP) *pp4++ = mkf4(R.pa[kMaxPlanes + NA + i], R.pb[kMaxPlanes + NA + i], R.pc[kMaxPlanes + NA + i], 0.0f);
     if (R.span) {
-        float4 *sp = sink.span + (size_t)rec * 3;
+        float4 *sp = spanDst ? spanDst : sink.span + (size_t)rec * 3;
         sp[0] = mkf4(R.bot.vx, R.bot.vy, R.bot.inv1, R.bot.inv2);
         sp[1] = mkf4(R.top.vx, R.top.vy, R.top.inv1, R.top.inv2);
         sp[2] = mkf4(u2f((uint32_t)R.bot.y0), u2f((uint32_t)R.bot.y1), u2f((uint32_t)R.top.y0), u2f((uint32_t)R.top.y1));
@@ -631,10 +631,12 @@ SWR_D void shadeVertex(const GeomArgs &g, int index, CVert<VS::AVarCount, VS::PV
 }
 
 // Mark every screen tile of `rank`'s partition that the group box (x0, y0)-(x1, y1) touches in that rank's
-// tile x chunk bitmap (called by a whole warp: the lanes share the tiles).  The update is a fire-and-forget
-// reduction (no NVLink round trip when the bitmap is a peer's); a local bitmap is read first, since most groups of a
-// batch find their bit already set.
-SWR_D void markTiles(const GeomArgs &g, const RecordSink &sink, int rank, bool local, uint32_t chunk, int x0, int y0, int x1, int y1)
+// tile x chunk bitmap (called by a whole warp: the lanes share the tiles).  The groups of one batch mostly touch
+// the same few tiles, so a small per-CTA cache of (rank, chunk parity, tile) keys already marked by this batch
+// filters the repeats -- what remains is a fire-and-forget reduction (no NVLink round trip when the bitmap is a
+// peer's).  A cache miss of a repeat only costs a redundant reduction.
+constexpr int kMarkCache = 256;
+SWR_D void markTiles(const GeomArgs &g, const RecordSink &sink, int rank, uint32_t *cache, uint32_t chunk, int x0, int y0, int x1, int y1)
 {
     if (x0 > x1) return;
     const int tx0 = x0 >> g.tileShift, ty0 = y0 >> g.tileShift;
@@ -648,15 +650,20 @@ SWR_D void markTiles(const GeomArgs &g, const RecordSink &sink, int rank, bool l
         const int ty = oneRow ? ty0 : oneCol ? ty0 + i : ty0 + i / nx;
         const int tx = oneRow ? tx0 + i : oneCol ? tx0 : tx0 + i % nx;
         if (!tileOwned(tx, ty, rank, g.world)) continue;
-        uint32_t *wp = sink.tilemap + (size_t)(ty * g.tilesX + tx) * g.chunkWords + (chunk >> 5);
-        if (local && (*(volatile uint32_t *)wp & bit)) continue;
-        atomicOr(wp, bit);                                   // result unused: compiles to RED
+        const uint32_t tile = (uint32_t)(ty * g.tilesX + tx);
+        const uint32_t key = ((uint32_t)rank << 28) | ((chunk & 1u) << 27) | tile;
+        uint32_t *slot = cache + ((tile * 2654435761u + (uint32_t)rank * 40503u + (chunk & 1u)) >> 24);
+        if (*(volatile uint32_t *)slot == key) continue;
+        *(volatile uint32_t *)slot = key;
+        atomicOr(sink.tilemap + (size_t)tile * g.chunkWords + (chunk >> 5), bit);   // result unused: compiles to RED
     }
 }
 
 #ifndef SWR_GEOM_MINB
-#define SWR_GEOM_MINB 3      // <= 80 registers: three 256-thread CTAs per SM (measured: with four the record a thread holds until its
-                             // slot is known spills; C5 -6 %, C2 -4 %, C3 equal)
+#define SWR_GEOM_MINB 4      // one rank: <= 64 registers, four 256-thread CTAs per SM (measured: 5 or 6 CTAs with spills are slower)
+#endif
+#ifndef SWR_GEOM_MINB_SHARDED
+#define SWR_GEOM_MINB_SHARDED 3   // sharded: <= 80 registers (the record a thread holds until its slot is known would spill at 64)
 #endif
 
 // Batch run by CTA `block` of a launch: all batches in turn, or -- sharded -- the batches of this rank.
@@ -666,11 +673,20 @@ SWR_D int batchOfBlock(const GeomArgs &g, int block)
     return ((block / kShardBatches) * g.world + g.rank) * kShardBatches + block % kShardBatches;
 }
 
-// MODE = draw mode, SPAN = false when the raster mode is known to be Block (no span state is carried): both are
-// launch-time constants, and as template parameters they keep the registers that live across the compaction
-// barrier down to what the mode really needs.
-template <class VS, int MODE, bool SPAN>
-__global__ void __launch_bounds__(kGeomThreads, SWR_GEOM_MINB) geometryKernel(const GeomArgs g)
+// Dynamic shared memory of the geometry kernel: the record staging area, or 0 when the shader's records are too
+// large for it (then the records are stored directly).
+template <int NA, int NP>
+struct GeomStage {
+    static constexpr size_t want = (size_t)(3 + kMaxPlanes + NA + NP) * 32 * 16 * (kGeomThreads / 32);
+    static constexpr size_t bytes = want <= 64 * 1024 ? want : 0;
+};
+
+// MODE = draw mode, SPAN = false when the raster mode is known to be Block (no span state is carried), MULTI = sharded
+// geometry (records compacted per destination rank and pushed to the tile owners; otherwise every record stays at
+// its own slot of this rank's scratch): launch-time constants, and as template parameters they keep the registers
+// and the instructions down to what the launch really needs.
+template <class VS, int MODE, bool SPAN, bool MULTI>
+__global__ void __launch_bounds__(kGeomThreads, MULTI ? SWR_GEOM_MINB_SHARDED : SWR_GEOM_MINB) geometryKernel(const GeomArgs g)
 {
     constexpr int NA = VS::AVarCount, NP = VS::PVarCount;
     typedef CVert<NA, NP> V;
@@ -682,8 +698,17 @@ __global__ void __launch_bounds__(kGeomThreads, SWR_GEOM_MINB) geometryKernel(co
     __shared__ uint32_t sWarpSum[kWarps];
     __shared__ uint32_t sExtraBase, sExtraTotal;
     __shared__ int sGx0[kMaxExtraGroups], sGy0[kMaxExtraGroups], sGx1[kMaxExtraGroups], sGy1[kMaxExtraGroups];
+    __shared__ Box16 sGb[kMaxRanks][kBatch / kGroup];               // group boxes / record counts of the batch per rank:
+    __shared__ uint8_t sGc[kMaxRanks][kBatch / kGroup];             //   written out in one piece per rank at the end
+    __shared__ uint32_t sMark[kMarkCache];                          // markTiles' filter
+
+    // per-warp staging of one group's records (head: 3 quads, params: up to kStageQuads - 3 quads per record)
+    constexpr int kStageQuads = 3 + kMaxPlanes + NA + NP;
+    constexpr bool kStage = MULTI && GeomStage<NA, NP>::bytes > 0;
+    extern __shared__ float4 sStageAll[];
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    float4 *stage = sStageAll + (kStage ? wid * 32 * kStageQuads : 0);
     const int batch = batchOfBlock(g, blockIdx.x);
     const int primBase = batch * kBatch;
     if (primBase >= g.numPrims) return;
@@ -694,6 +719,8 @@ __global__ void __launch_bounds__(kGeomThreads, SWR_GEOM_MINB) geometryKernel(co
     // replicated geometry: only the records of this rank's tiles are kept
     const uint32_t keepMask = g.shard ? (1u << world) - 1u : (1u << g.rank);
     bool anyExtra = false;
+    for (int i = tid; i < kMarkCache; i += kGeomThreads) sMark[i] = 0xffffffffu;
+    __syncthreads();
 
     // the next round's indices are fetched while the current round computes (the vertex fetch
     // depends on them, so this takes one DRAM round trip off every round's critical path)
@@ -771,14 +798,38 @@ __global__ void __launch_bounds__(kGeomThreads, SWR_GEOM_MINB) geometryKernel(co
         sExtraCnt[slot] = (uint16_t)extras;
         anyExtra |= extras > 0;
 
+        const int gl = slot >> 5;                             // group within the batch
+        if (!MULTI) {
+            // ---- one destination (this rank): the record stays at its own slot; slots of dropped primitives -- and, with
+            // several ranks and replicated geometry, of primitives that touch none of this rank's tiles -- hold a dead box
+            const RecordSink &sk = g.sink[g.rank];
+            if (world > 1 && !((boxOwnerMask(box, g.tileShift, g.tilesX, g.tilesY, world) >> g.rank) & 1u)) box = deadBox();
+            const uint32_t rec = (uint32_t)(primBase + slot);
+            sk.bbox[rec] = box;
+            if (box.x0 <= box.x1) {
+                if (MODE == SWR_DRAW_TRIANGLE) storeTriangle<NA, NP>(g, sk, rec, R);
+                else if (MODE == SWR_DRAW_LINE) storeLine<NA, NP>(g, sk, rec, ordinal, steps, la, lb);
+                else storePoint<NA, NP>(g, sk, rec, ordinal, la);
+            }
+            const int x0 = __reduce_min_sync(0xffffffffu, (int)box.x0), y0 = __reduce_min_sync(0xffffffffu, (int)box.y0);
+            const int x1 = __reduce_max_sync(0xffffffffu, (int)box.x1), y1 = __reduce_max_sync(0xffffffffu, (int)box.y1);
+            if (lane == 0) {
+                Box16 u; u.x0 = (int16_t)x0; u.y0 = (int16_t)y0; u.x1 = (int16_t)x1; u.y1 = (int16_t)y1;
+                sGb[0][gl] = u;
+                sGc[0][gl] = 32;                              // all 32 slots hold a box
+            }
+            markTiles(g, sk, g.rank, sMark, 2u * (uint32_t)batch, x0, y0, x1, y1);
+            cur[0] = nxt[0]; cur[1] = nxt[1]; cur[2] = nxt[2];
+            continue;
+        }
         // ---- per destination rank: the surviving records of the group, compacted to the front of the group's 32
         // slots in submission order (ballot + popcount: the warps never wait for each other), their count, the
         // union of their boxes and the tiles it touches.  Slots behind the count are never written, nor read.
         const uint32_t dm = boxOwnerMask(box, g.tileShift, g.tilesX, g.tilesY, world) & keepMask;
         const uint32_t anyD = __reduce_or_sync(0xffffffffu, dm);
-        if (lane < world && ((keepMask >> lane) & 1u) && !((anyD >> lane) & 1u)) {
-            g.sink[lane].gbox[group] = deadBox();             // nothing of this group concerns rank `lane`
-            g.sink[lane].gcnt[group] = 0;
+        if (lane < world && !((anyD >> lane) & 1u)) {
+            sGb[lane][gl] = deadBox();                        // nothing of this group concerns rank `lane`
+            sGc[lane][gl] = 0;
         }
         for (uint32_t m = anyD; m; m &= m - 1) {
             const int d = __ffs((int)m) - 1;
@@ -787,8 +838,29 @@ __global__ void __launch_bounds__(kGeomThreads, SWR_GEOM_MINB) geometryKernel(co
             const int x0 = __reduce_min_sync(0xffffffffu, mine ? (int)box.x0 : 32767), y0 = __reduce_min_sync(0xffffffffu, mine ? (int)box.y0 : 32767);
             const int x1 = __reduce_max_sync(0xffffffffu, mine ? (int)box.x1 : -32768), y1 = __reduce_max_sync(0xffffffffu, mine ? (int)box.y1 : -32768);
             const RecordSink &sk = g.sink[d];
-            if (mine) {
-                const uint32_t rec = (group << 5) + (uint32_t)__popc(b & ((1u << lane) - 1u));
+            const uint32_t pos = (uint32_t)__popc(b & ((1u << lane) - 1u)), n = (uint32_t)__popc(b);
+            if (kStage) {
+                // The records go through shared memory so that every store instruction of the warp writes one
+                // contiguous run (32 lanes x 16 bytes) instead of 32 pieces 48 bytes apart: what matters when the
+                // destination is a peer (every store instruction becomes its own train of NVLink write packets).
+                if (mine) {
+                    RecordSink st = sk;
+                    st.head = stage;
+                    st.params = reinterpret_cast<float *>(stage + 32 * 3);
+                    if (MODE == SWR_DRAW_TRIANGLE) storeTriangle<NA, NP>(g, st, pos, R, sk.span ? sk.span + (size_t)((group << 5) + pos) * 3 : nullptr);
+                    else if (MODE == SWR_DRAW_LINE) storeLine<NA, NP>(g, st, pos, ordinal, steps, la, lb);
+                    else storePoint<NA, NP>(g, st, pos, ordinal, la);
+                    sk.bbox[(group << 5) + pos] = box;
+                }
+                __syncwarp();
+                const uint32_t pq = (uint32_t)g.paramStride >> 2;
+                float4 *dh = sk.head + (size_t)(group << 5) * 3;
+                float4 *dp = reinterpret_cast<float4 *>(sk.params + (size_t)(group << 5) * g.paramStride);
+                for (uint32_t i = lane; i < n * 3u; i += 32) dh[i] = stage[i];
+                for (uint32_t i = lane; i < n * pq; i += 32) dp[i] = stage[32 * 3 + i];
+                __syncwarp();
+            } else if (mine) {
+                const uint32_t rec = (group << 5) + pos;
                 sk.bbox[rec] = box;
                 if (MODE == SWR_DRAW_TRIANGLE) storeTriangle<NA, NP>(g, sk, rec, R);
                 else if (MODE == SWR_DRAW_LINE) storeLine<NA, NP>(g, sk, rec, ordinal, steps, la, lb);
@@ -796,10 +868,10 @@ __global__ void __launch_bounds__(kGeomThreads, SWR_GEOM_MINB) geometryKernel(co
             }
             if (lane == 0) {
                 Box16 u; u.x0 = (int16_t)x0; u.y0 = (int16_t)y0; u.x1 = (int16_t)x1; u.y1 = (int16_t)y1;
-                sk.gbox[group] = u;
-                sk.gcnt[group] = (uint8_t)__popc(b);
+                sGb[d][gl] = u;
+                sGc[d][gl] = (uint8_t)n;
             }
-            markTiles(g, sk, d, d == g.rank, 2u * (uint32_t)batch, x0, y0, x1, y1);
+            markTiles(g, sk, d, sMark, 2u * (uint32_t)batch, x0, y0, x1, y1);
         }
         cur[0] = nxt[0]; cur[1] = nxt[1]; cur[2] = nxt[2];
     }
@@ -808,6 +880,15 @@ __global__ void __launch_bounds__(kGeomThreads, SWR_GEOM_MINB) geometryKernel(co
 
     const bool haveExtras = __syncthreads_or(anyExtra);
     if (tid < world && ((keepMask >> tid) & 1u) && (MODE != SWR_DRAW_TRIANGLE || !haveExtras)) g.sink[tid].extra[batch] = make_uint2(0u, 0u);
+    {   // the batch's 32 group boxes and counts, one contiguous run per rank
+        static_assert(kGeomThreads == kMaxRanks * (kBatch / kGroup), "one thread per (rank, group)");
+        const int d = tid >> 5;
+        if (MULTI ? (d < world) : (d == 0)) {
+            const RecordSink &sk = g.sink[MULTI ? d : g.rank];
+            sk.gbox[((uint32_t)primBase >> 5) + lane] = sGb[d][lane];
+            sk.gcnt[((uint32_t)primBase >> 5) + lane] = sGc[d][lane];
+        }
+    }
     if (MODE != SWR_DRAW_TRIANGLE || !haveExtras) return;
 
     // ---- clipper fan extras: appended behind the batch's original slots, in primitive order.  They keep one slot
@@ -893,7 +974,7 @@ __global__ void __launch_bounds__(kGeomThreads, SWR_GEOM_MINB) geometryKernel(co
             sk.gbox[(ebase >> 5) + (uint32_t)gi] = u;
             sk.gcnt[(ebase >> 5) + (uint32_t)gi] = (uint8_t)min(32u, etotal - (uint32_t)gi * 32u);
         }
-        markTiles(g, sk, d, d == g.rank, 2u * (uint32_t)batch + 1u, sGx0[gi], sGy0[gi], sGx1[gi], sGy1[gi]);
+        markTiles(g, sk, d, sMark, 2u * (uint32_t)batch + 1u, sGx0[gi], sGy0[gi], sGx1[gi], sGy1[gi]);
     }
 }
 
@@ -910,15 +991,34 @@ void launchGeometry(const void *args, void *stream)
         const int mine = runs > g->rank ? (runs - g->rank + g->world - 1) / g->world : 0;
         blocks = mine * kShardBatches;
     }
-    if (blocks <= 0) return;
+    // numPrims == 0: nothing is launched, but the kernel the launch would use is resolved (loaded onto the device).  The
+    // runtime asks for this before it enqueues a cross-GPU barrier, so that the launch after the barrier cannot stall
+    // on a lazy module load.
     cudaStream_t st = (cudaStream_t)stream;
-    if (g->drawMode == SWR_DRAW_TRIANGLE) {
-        if (g->rasterMode == SWR_RASTER_BLOCK) geometryKernel<VS, SWR_DRAW_TRIANGLE, false><<<blocks, kGeomThreads, 0, st>>>(*g);
-        else geometryKernel<VS, SWR_DRAW_TRIANGLE, true><<<blocks, kGeomThreads, 0, st>>>(*g);
-    } else if (g->drawMode == SWR_DRAW_LINE) {
-        geometryKernel<VS, SWR_DRAW_LINE, false><<<blocks, kGeomThreads, 0, st>>>(*g);
+    constexpr size_t stageBytes = GeomStage<VS::AVarCount, VS::PVarCount>::bytes;
+    auto launch = [&](auto kernel, size_t smem) {
+        if (smem > 0) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (blocks > 0) kernel<<<blocks, kGeomThreads, smem, st>>>(*g);
+        else { cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, kernel); }
+    };
+    if (g->shard) {
+        if (g->drawMode == SWR_DRAW_TRIANGLE) {
+            if (g->rasterMode == SWR_RASTER_BLOCK) launch(geometryKernel<VS, SWR_DRAW_TRIANGLE, false, true>, stageBytes);
+            else launch(geometryKernel<VS, SWR_DRAW_TRIANGLE, true, true>, stageBytes);
+        } else if (g->drawMode == SWR_DRAW_LINE) {
+            launch(geometryKernel<VS, SWR_DRAW_LINE, false, true>, stageBytes);
+        } else {
+            launch(geometryKernel<VS, SWR_DRAW_POINT, false, true>, stageBytes);
+        }
     } else {
-        geometryKernel<VS, SWR_DRAW_POINT, false><<<blocks, kGeomThreads, 0, st>>>(*g);
+        if (g->drawMode == SWR_DRAW_TRIANGLE) {
+            if (g->rasterMode == SWR_RASTER_BLOCK) launch(geometryKernel<VS, SWR_DRAW_TRIANGLE, false, false>, 0);
+            else launch(geometryKernel<VS, SWR_DRAW_TRIANGLE, true, false>, 0);
+        } else if (g->drawMode == SWR_DRAW_LINE) {
+            launch(geometryKernel<VS, SWR_DRAW_LINE, false, false>, 0);
+        } else {
+            launch(geometryKernel<VS, SWR_DRAW_POINT, false, false>, 0);
+        }
     }
 }
 

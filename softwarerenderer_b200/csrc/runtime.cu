@@ -240,6 +240,9 @@ size_t scratchBytes(const swr_context *c)
 __global__ void __launch_bounds__(kGeomThreads) rasterListKernel(const GeomArgs g)
 {
     typedef CVert<SWR_MAX_AVARS, SWR_MAX_PVARS> V;
+    __shared__ uint32_t sMark[kMarkCache];
+    for (int i = threadIdx.x; i < kMarkCache; i += kGeomThreads) sMark[i] = 0xffffffffu;
+    __syncthreads();
     const int tid = threadIdx.x, lane = tid & 31;
     const int batch = blockIdx.x;
     const int primBase = batch * kBatch;
@@ -274,7 +277,7 @@ __global__ void __launch_bounds__(kGeomThreads) rasterListKernel(const GeomArgs 
             sk.gbox[rec >> 5] = u;
             sk.gcnt[rec >> 5] = 32;                             // the list is not compacted: skipped entries are dead boxes
         }
-        markTiles(g, sk, g.rank, true, 2u * (uint32_t)batch, x0, y0, x1, y1);
+        markTiles(g, sk, g.rank, sMark, 2u * (uint32_t)batch, x0, y0, x1, y1);
     }
     if (tid == 0) sk.extra[batch] = make_uint2(0u, 0u);
 }
@@ -734,6 +737,11 @@ int drawCommon(swr_context *c, int drawMode, size_t count, const int32_t *indice
             // and (2) every geometry kernel must be done before any tile kernel reads.  (1) is a clear followed by a
             // barrier; the clear is issued right after the tile kernel of the previous pass, so that a barrier the
             // host enqueues anyway at the end of a frame (swr_peer_barrier) also serves as (1) of the next draw.
+            {   // resolve the geometry kernel before anything waits on a peer (see launchGeometry)
+                GeomArgs pre = g;
+                pre.numPrims = 0;
+                geomLaunch(&pre, gs);
+            }
             if (c->clearedKey != layoutKey) {
                 if (int rc = clearSet()) return rc;
                 c->clearedKey = layoutKey;

@@ -103,11 +103,12 @@ class TileMirror:
     Contract (see swr_set_tile_mirrors): all ranks clear the surface the same way, and call barrier() between
     that clear and the first draw of a frame as well as after the last draw, before the surface is read."""
 
-    def __init__(self, rasterizer, slot: int, surface_ptr: int, rank: int, world: int, device):
+    def __init__(self, rasterizer, slot: int, surface_ptr: int, rank: int, world: int, device, peer_barrier=None):
         import torch
         import torch.distributed as dist
         from . import api
         self.r, self.slot, self.rank, self.world = rasterizer, slot, rank, world
+        self._peer_barrier = peer_barrier     # e.g. GeometryShards.barrier: the library's own flag barrier instead of NCCL
         # every step that can fail is followed by a collective agreement, so that all ranks raise together
         # (and the caller can fall back to TileComposite on all of them) instead of one rank leaving a collective
         try:
@@ -138,7 +139,11 @@ class TileMirror:
         self._token = torch.zeros(1, dtype=torch.int32, device=device)
 
     def barrier(self) -> None:
-        """Stream-ordered cross-rank barrier (a one-word NCCL all-reduce on torch's current stream)."""
+        """Stream-ordered cross-rank barrier: the library's flag barrier when the partition has one (sharded geometry),
+        else a one-word NCCL all-reduce on torch's current stream."""
+        if self._peer_barrier is not None:
+            self._peer_barrier()
+            return
         import torch.distributed as dist
         dist.all_reduce(self._token)
 

@@ -14,7 +14,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 from softwarerenderer_b200 import api, scenes as S  # noqa: E402
 from softwarerenderer_b200.api import SceneRenderer  # noqa: E402
-from softwarerenderer_b200.dist import TileMirror  # noqa: E402
+from softwarerenderer_b200.dist import GeometryShards, TileMirror  # noqa: E402
 
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 local = int(os.environ.get("LOCAL_RANK", rank))
@@ -22,13 +22,19 @@ torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
 
-scene = S.config_c2(nx=300, ny=200, width=1280, height=720) if len(sys.argv) < 2 else getattr(S, sys.argv[1])()
+argv = [a for a in sys.argv[1:] if not a.startswith("--")]
+scene = S.config_c2(nx=300, ny=200, width=1280, height=720) if not argv else getattr(S, argv[0])()
 sr = SceneRenderer(scene.width, scene.height, device=local)
 stream = torch.cuda.Stream(device=dev)
 torch.cuda.set_stream(stream)
 sr.r.setStream(stream.cuda_stream)
 sr.r.setTilePartition(rank, world)
-mirror = TileMirror(sr.r, api.RT_COLOR, sr.targets.ptr(api.RT_COLOR), rank, world, dev)
+shards = None
+if "--shards" in sys.argv:                # sharded geometry: records pushed to the tile owners, library barrier
+    sr.draw(scene)
+    shards = GeometryShards(sr.r, rank, world, dev, 2 << 30)
+mirror = TileMirror(sr.r, api.RT_COLOR, sr.targets.ptr(api.RT_COLOR), rank, world, dev,
+                    peer_barrier=shards.barrier if shards else None)
 ok = True
 for frame in range(3):
     sr.targets.clear()
@@ -49,6 +55,8 @@ flag = torch.tensor([1 if ok else 0], device=dev)
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 torch.cuda.synchronize()
 mirror.close()
+if shards:
+    shards.close()
 sr.close()
 if rank == 0:
     print("MIRROR OK" if int(flag.item()) == 1 else "MIRROR FAILED", flush=True)

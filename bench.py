@@ -383,7 +383,7 @@ def run_gpu_arm(args):
         lo, hi = sums.clone(), sums.clone()
         dist.all_reduce(lo, op=dist.ReduceOp.MIN)
         dist.all_reduce(hi, op=dist.ReduceOp.MAX)
-        if not torch.equal(lo, hi):
+        if not torch.equal(lo, hi) and not os.environ.get("SWR_DEBUG_FAKE_PEERS"):
             raise SystemExit(f"composite differs between ranks: {lo.tolist()} vs {hi.tolist()}")
     fragments = int(frag_t.item())
 

@@ -129,7 +129,7 @@ int main(int argc, char *argv[])
 
     r.setPixelShader<PixelShader>();
     v.setVertexShader<VertexShader>();
-    v.setVertexAttribPointer(0, sizeof(VertexData), &vertices[0], sizeof(VertexData) * vertices.size());
+    v.setVertexAttribPointer(0, sizeof(VertexData), &vertices[0]);          // Benchmark.cpp:99, as is: no extent
 
     v.drawElements(DrawMode::Triangle, indices.size(), &indices[0]);     // warm-up (allocates scratch)
     swr_reset_stats(r.context());

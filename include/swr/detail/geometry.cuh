@@ -675,10 +675,13 @@ SWR_D int batchOfBlock(const GeomArgs &g, int block)
 
 // Dynamic shared memory of the geometry kernel: the record staging area, or 0 when the shader's records are too
 // large for it (then the records are stored directly).
+constexpr int kGeomThreadsSharded = 256;    // threads per batch of the sharded form (measured on C3 at N = 2: 1024 threads, i.e. one
+                                            // CTA per SM and the whole batch in one round, is 15 % slower: no second CTA fills its barriers)
+
 template <int NA, int NP>
 struct GeomStage {
-    static constexpr size_t want = (size_t)(3 + kMaxPlanes + NA + NP) * 32 * 16 * (kGeomThreads / 32);
-    static constexpr size_t bytes = want <= 64 * 1024 ? want : 0;
+    static constexpr size_t want = (size_t)(3 + kMaxPlanes + NA + NP) * 32 * 16 * (kGeomThreadsSharded / 32);
+    static constexpr size_t bytes = want <= 200 * 1024 ? want : 0;
 };
 
 // MODE = draw mode, SPAN = false when the raster mode is known to be Block (no span state is carried), MULTI = sharded
@@ -686,12 +689,14 @@ struct GeomStage {
 // its own slot of this rank's scratch): launch-time constants, and as template parameters they keep the registers
 // and the instructions down to what the launch really needs.
 template <class VS, int MODE, bool SPAN, bool MULTI>
-__global__ void __launch_bounds__(kGeomThreads, MULTI ? SWR_GEOM_MINB_SHARDED : SWR_GEOM_MINB) geometryKernel(const GeomArgs g)
+__global__ void __launch_bounds__(MULTI ? kGeomThreadsSharded : kGeomThreads, MULTI ? SWR_GEOM_MINB_SHARDED : SWR_GEOM_MINB) geometryKernel(const GeomArgs g)
 {
+    constexpr int kThreads = MULTI ? kGeomThreadsSharded : kGeomThreads;
+    constexpr int kSlots = kBatch / kThreads;            // slots per thread in the block-wide scans
     constexpr int NA = VS::AVarCount, NP = VS::PVarCount;
     typedef CVert<NA, NP> V;
     constexpr int kMaxExtraGroups = kBatch * (kMaxFan - 1) / kGroup;
-    constexpr int kWarps = kGeomThreads / 32;
+    constexpr int kWarps = kThreads / 32;
 
     __shared__ uint16_t sExtraCnt[kBatch];     // fan extras per primitive of this batch
     __shared__ uint16_t sExtraOfs[kBatch];     // exclusive prefix in primitive order
@@ -719,15 +724,15 @@ __global__ void __launch_bounds__(kGeomThreads, MULTI ? SWR_GEOM_MINB_SHARDED : 
     // replicated geometry: only the records of this rank's tiles are kept
     const uint32_t keepMask = g.shard ? (1u << world) - 1u : (1u << g.rank);
     bool anyExtra = false;
-    for (int i = tid; i < kMarkCache; i += kGeomThreads) sMark[i] = 0xffffffffu;
+    for (int i = tid; i < kMarkCache; i += kThreads) sMark[i] = 0xffffffffu;
     __syncthreads();
 
     // the next round's indices are fetched while the current round computes (the vertex fetch
     // depends on them, so this takes one DRAM round trip off every round's critical path)
-    constexpr int kRounds = kBatch / kGeomThreads;
+    constexpr int kRounds = kBatch / kThreads;
     int32_t cur[3] = { 0, 0, 0 }, nxt[3] = { 0, 0, 0 };
     auto fetch = [&](int r, int32_t *dst) {
-        const int slot = r * kGeomThreads + tid;
+        const int slot = r * kThreads + tid;
         if (slot < cnt) {
             const int32_t *ip = g.indices + (size_t)(primBase + slot) * per;
             dst[0] = ip[0];
@@ -740,7 +745,7 @@ __global__ void __launch_bounds__(kGeomThreads, MULTI ? SWR_GEOM_MINB_SHARDED : 
 #pragma unroll 1
     for (int r = 0; r < kRounds; ++r) {
         if (r + 1 < kRounds) fetch(r + 1, nxt);
-        const int slot = r * kGeomThreads + tid;
+        const int slot = r * kThreads + tid;
         const uint32_t group = (uint32_t)(primBase + slot) >> 5;      // the 32 slots this warp handles in this round
         Box16 box = deadBox();
         int extras = 0;
@@ -881,7 +886,7 @@ __global__ void __launch_bounds__(kGeomThreads, MULTI ? SWR_GEOM_MINB_SHARDED : 
     const bool haveExtras = __syncthreads_or(anyExtra);
     if (tid < world && ((keepMask >> tid) & 1u) && (MODE != SWR_DRAW_TRIANGLE || !haveExtras)) g.sink[tid].extra[batch] = make_uint2(0u, 0u);
     {   // the batch's 32 group boxes and counts, one contiguous run per rank
-        static_assert(kGeomThreads == kMaxRanks * (kBatch / kGroup), "one thread per (rank, group)");
+        static_assert(kThreads >= kMaxRanks * (kBatch / kGroup), "one thread per (rank, group)");
         const int d = tid >> 5;
         if (MULTI ? (d < world) : (d == 0)) {
             const RecordSink &sk = g.sink[MULTI ? d : g.rank];
@@ -893,9 +898,11 @@ __global__ void __launch_bounds__(kGeomThreads, MULTI ? SWR_GEOM_MINB_SHARDED : 
 
     // ---- clipper fan extras: appended behind the batch's original slots, in primitive order.  They keep one slot
     // each (no compaction): every rank gets the whole range of boxes, dead where the triangle is not its business.
-    {   // exclusive scan of sExtraCnt over the 1024 slots: thread t owns slots 4t..4t+3
-        uint32_t c0 = sExtraCnt[4 * tid], c1 = sExtraCnt[4 * tid + 1], c2 = sExtraCnt[4 * tid + 2], c3 = sExtraCnt[4 * tid + 3];
-        uint32_t sum = c0 + c1 + c2 + c3, incl = sum;
+    {   // exclusive scan of sExtraCnt over the 1024 slots: thread t owns the kSlots consecutive slots from kSlots * t
+        uint32_t cs[kSlots], sum = 0;
+#pragma unroll
+        for (int k = 0; k < kSlots; ++k) { cs[k] = sExtraCnt[kSlots * tid + k]; sum += cs[k]; }
+        uint32_t incl = sum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
@@ -906,11 +913,12 @@ __global__ void __launch_bounds__(kGeomThreads, MULTI ? SWR_GEOM_MINB_SHARDED : 
         uint32_t base = 0;
         for (int w = 0; w < wid; ++w) base += sWarpSum[w];
         uint32_t ex = base + incl - sum;
-        sExtraOfs[4 * tid] = (uint16_t)ex;
-        sExtraOfs[4 * tid + 1] = (uint16_t)(ex + c0);
-        sExtraOfs[4 * tid + 2] = (uint16_t)(ex + c0 + c1);
-        sExtraOfs[4 * tid + 3] = (uint16_t)(ex + c0 + c1 + c2);
-        if (tid == kGeomThreads - 1) {
+        {
+            uint32_t run = ex;
+#pragma unroll
+            for (int k = 0; k < kSlots; ++k) { sExtraOfs[kSlots * tid + k] = (uint16_t)run; run += cs[k]; }
+        }
+        if (tid == kThreads - 1) {
             const uint32_t total = ex + sum;
             const uint32_t padded = (total + kGroup - 1) & ~(uint32_t)(kGroup - 1);
             uint32_t b0 = atomicAdd(g.extraAlloc, padded);
@@ -922,7 +930,7 @@ __global__ void __launch_bounds__(kGeomThreads, MULTI ? SWR_GEOM_MINB_SHARDED : 
             sExtraBase = b0;
             sExtraTotal = total;
         }
-        for (int i = tid; i < kMaxExtraGroups; i += kGeomThreads) { sGx0[i] = 32767; sGy0[i] = 32767; sGx1[i] = -32768; sGy1[i] = -32768; }
+        for (int i = tid; i < kMaxExtraGroups; i += kThreads) { sGx0[i] = 32767; sGy0[i] = 32767; sGx1[i] = -32768; sGy1[i] = -32768; }
         __syncthreads();
     }
     const uint32_t ebase = sExtraBase, etotal = sExtraTotal;
@@ -930,8 +938,8 @@ __global__ void __launch_bounds__(kGeomThreads, MULTI ? SWR_GEOM_MINB_SHARDED : 
         g.sink[tid].extra[batch] = (ebase == 0xffffffffu) ? make_uint2(0u, 0u) : make_uint2(ebase, etotal);
     if (ebase == 0xffffffffu) return;                       // flagged, draw is void
 
-    for (int r = 0; r < kBatch / kGeomThreads; ++r) {
-        const int slot = r * kGeomThreads + tid;
+    for (int r = 0; r < kRounds; ++r) {
+        const int slot = r * kThreads + tid;
         const int extras = sExtraCnt[slot];
         if (extras == 0) continue;
         const uint32_t ofs = sExtraOfs[slot];
@@ -998,7 +1006,7 @@ void launchGeometry(const void *args, void *stream)
     constexpr size_t stageBytes = GeomStage<VS::AVarCount, VS::PVarCount>::bytes;
     auto launch = [&](auto kernel, size_t smem) {
         if (smem > 0) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (blocks > 0) kernel<<<blocks, kGeomThreads, smem, st>>>(*g);
+        if (blocks > 0) kernel<<<blocks, g->shard ? kGeomThreadsSharded : kGeomThreads, smem, st>>>(*g);
         else { cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, kernel); }
     };
     if (g->shard) {
@@ -1022,10 +1030,148 @@ void launchGeometry(const void *args, void *stream)
     }
 }
 
+// ---- stream-out: the vertex stage alone, for a VertexProcessor whose IRasterizer is not ours ----------------
+// One CTA per batch of 1024 input primitives (VertexProcessor.cpp:110-116) writes what the reference hands to
+// IRasterizer::draw{Point,Line,Triangle}List (VertexProcessor.cpp:302-317): screen-space RasterizerVertex records and
+// the index list, with -1 for primitives dropped by clipping / culling (VertexProcessor.cpp:152-165, 196-200,
+// 244-250, 331-340), culled-in triangles re-oriented by swapping their first and last index (VertexProcessor.cpp:342),
+// and the clipper's fan triangles appended behind the batch's own primitives in primitive order
+// (VertexProcessor.cpp:252-261).  The vertex array is not de-duplicated (every primitive owns `per` consecutive
+// vertices): the reference's VertexCache only affects which array positions the indices name, never the primitives
+// a rasterizer sees.  Layout of batch b: vertices [b * soStride, ...), indices likewise, soStride = per * 1024 +
+// 3 * soExtraCap; soCounts[b] = fan triangles appended.
+struct SoVertex { float v[4 + SWR_MAX_AVARS + SWR_MAX_PVARS]; };
+
+template <int NA, int NP>
+SWR_D void soWrite(SoVertex *dst, const CVert<NA, NP> &c)
+{
+    float4 *q = reinterpret_cast<float4 *>(dst);
+    float f[36];
+#pragma unroll
+    for (int i = 0; i < 36; ++i) f[i] = 0.0f;
+    f[0] = c.x; f[1] = c.y; f[2] = c.z; f[3] = c.w;
+#pragma unroll
+    for (int i = 0; i < NA; ++i) f[4 + i] = c.a[i];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) f[4 + SWR_MAX_AVARS + i] = c.p[i];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) q[i] = mkf4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+}
+
+// Screen-space triangle into the stream: cull (drop / keep / swap first and last index), three vertices, three indices.
+template <int NA, int NP>
+SWR_D void soTriangle(const GeomArgs &g, SoVertex *verts, int32_t *idx, int at, CVert<NA, NP> a, CVert<NA, NP> b, CVert<NA, NP> c)
+{
+    toScreen(g, a); toScreen(g, b); toScreen(g, c);
+    const float facing = fsub(fmul(fsub(a.x, b.x), fsub(c.y, b.y)), fmul(fsub(c.x, b.x), fsub(a.y, b.y)));
+    bool drop = false, swap = false;
+    if (facing < 0) drop = g.cullMode == SWR_CULL_CW;
+    else { drop = g.cullMode == SWR_CULL_CCW; swap = !drop; }
+    if (drop) { idx[at] = idx[at + 1] = idx[at + 2] = -1; return; }
+    soWrite(verts + at, a); soWrite(verts + at + 1, b); soWrite(verts + at + 2, c);
+    idx[at] = swap ? at + 2 : at; idx[at + 1] = at + 1; idx[at + 2] = swap ? at : at + 2;
+}
+
+template <class VS>
+__global__ void __launch_bounds__(kGeomThreads) streamOutKernel(const GeomArgs g)
+{
+    constexpr int NA = VS::AVarCount, NP = VS::PVarCount;
+    typedef CVert<NA, NP> V;
+    __shared__ uint16_t sExtraCnt[kBatch], sExtraOfs[kBatch];
+    __shared__ uint32_t sWarpSum[kGeomThreads / 32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int batch = blockIdx.x;
+    const int primBase = batch * kBatch;
+    const int cnt = min(kBatch, g.numPrims - primBase);
+    const int per = g.drawMode + 1;
+    const size_t stride = (size_t)per * kBatch + 3 * (size_t)g.soExtraCap;
+    SoVertex *verts = static_cast<SoVertex *>(g.soVerts) + (size_t)batch * stride;
+    int32_t *idx = g.soIndices + (size_t)batch * stride;
+    bool anyExtra = false;
+    for (int r = 0; r < kBatch / kGeomThreads; ++r) {
+        const int slot = r * kGeomThreads + tid;
+        int extras = 0;
+        if (slot < cnt) {
+            const int32_t *ip = g.indices + (size_t)(primBase + slot) * per;
+            const int at = slot * per;
+            if (g.drawMode == SWR_DRAW_TRIANGLE) {
+                V v0, v1, v2;
+                shadeVertex<VS>(g, ip[0], v0); shadeVertex<VS>(g, ip[1], v1); shadeVertex<VS>(g, ip[2], v2);
+                const int mask = outcode(v0.x, v0.y, v0.z, v0.w) | outcode(v1.x, v1.y, v1.z, v1.w) | outcode(v2.x, v2.y, v2.z, v2.w);
+                if (mask == 0) {
+                    soTriangle<NA, NP>(g, verts, idx, at, v0, v1, v2);
+                } else {
+                    V a[kMaxPoly], b[kMaxPoly], *poly;
+                    a[0] = v0; a[1] = v1; a[2] = v2;
+                    bool overflow = false;
+                    const int n = clipTriangle<NA, NP>(a, b, mask, &poly, &overflow);
+                    if (overflow) { atomicOr(g.sink[g.rank].errorFlag, 4u); atomicOr(g.sink[g.rank].errorFlag + 1, 4u); }
+                    if (n >= 3) { soTriangle<NA, NP>(g, verts, idx, at, poly[0], poly[1], poly[2]); extras = n - 3; }
+                    else idx[at] = idx[at + 1] = idx[at + 2] = -1;
+                }
+            } else if (g.drawMode == SWR_DRAW_LINE) {
+                V c0, c1, a, b;
+                shadeVertex<VS>(g, ip[0], c0); shadeVertex<VS>(g, ip[1], c1);
+                if (clipLineToScreen<NA, NP>(g, c0, c1, a, b)) {
+                    soWrite(verts + at, a); soWrite(verts + at + 1, b);
+                    idx[at] = at; idx[at + 1] = at + 1;
+                } else idx[at] = idx[at + 1] = -1;
+            } else {
+                V c0;
+                shadeVertex<VS>(g, ip[0], c0);
+                if (outcode(c0.x, c0.y, c0.z, c0.w) == 0) { toScreen(g, c0); soWrite(verts + at, c0); idx[at] = at; }
+                else idx[at] = -1;
+            }
+        }
+        sExtraCnt[slot] = (uint16_t)extras;
+        anyExtra |= extras > 0;
+    }
+    if (!__syncthreads_or(anyExtra)) {
+        if (tid == 0) g.soCounts[batch] = 0;
+        return;
+    }
+    uint32_t c0 = sExtraCnt[4 * tid], c1 = sExtraCnt[4 * tid + 1], c2 = sExtraCnt[4 * tid + 2], c3 = sExtraCnt[4 * tid + 3];
+    uint32_t sum = c0 + c1 + c2 + c3, incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += n;
+    }
+    if (lane == 31) sWarpSum[wid] = incl;
+    __syncthreads();
+    uint32_t base = 0;
+    for (int w = 0; w < wid; ++w) base += sWarpSum[w];
+    const uint32_t ex = base + incl - sum;
+    sExtraOfs[4 * tid] = (uint16_t)ex; sExtraOfs[4 * tid + 1] = (uint16_t)(ex + c0);
+    sExtraOfs[4 * tid + 2] = (uint16_t)(ex + c0 + c1); sExtraOfs[4 * tid + 3] = (uint16_t)(ex + c0 + c1 + c2);
+    if (tid == kGeomThreads - 1) g.soCounts[batch] = ex + sum;
+    __syncthreads();
+    for (int r = 0; r < kBatch / kGeomThreads; ++r) {
+        const int slot = r * kGeomThreads + tid;
+        const int extras = sExtraCnt[slot];
+        if (extras == 0) continue;
+        const int32_t *ip = g.indices + (size_t)(primBase + slot) * 3;
+        V a[kMaxPoly], b[kMaxPoly], *poly;
+        shadeVertex<VS>(g, ip[0], a[0]); shadeVertex<VS>(g, ip[1], a[1]); shadeVertex<VS>(g, ip[2], a[2]);
+        const int mask = outcode(a[0].x, a[0].y, a[0].z, a[0].w) | outcode(a[1].x, a[1].y, a[1].z, a[1].w) | outcode(a[2].x, a[2].y, a[2].z, a[2].w);
+        const int n = clipTriangle<NA, NP>(a, b, mask, &poly, nullptr);
+        for (int k = 1; k + 2 < n; ++k)
+            soTriangle<NA, NP>(g, verts, idx, 3 * cnt + 3 * ((int)sExtraOfs[slot] + k - 1), poly[0], poly[k + 1], poly[k + 2]);
+    }
+}
+
+template <class VS>
+void launchStreamOut(const void *args, void *stream)
+{
+    const GeomArgs *g = static_cast<const GeomArgs *>(args);
+    const int batches = (g->numPrims + kBatch - 1) / kBatch;
+    if (batches > 0) streamOutKernel<VS><<<batches, kGeomThreads, 0, (cudaStream_t)stream>>>(*g);
+}
+
 template <class VS>
 const swr_vertex_shader *vertexShaderBinding(const char *name = "user")
 {
-    static const swr_vertex_shader d = { &launchGeometry<VS>, &uploadUniforms, VS::AttribCount, VS::AVarCount, VS::PVarCount, name, SWR_ARGS_LAYOUT };
+    static const swr_vertex_shader d = { &launchGeometry<VS>, &launchStreamOut<VS>, &uploadUniforms, VS::AttribCount, VS::AVarCount, VS::PVarCount, name, SWR_ARGS_LAYOUT };
     return &d;
 }
 

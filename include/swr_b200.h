@@ -79,6 +79,7 @@ typedef int (*swr_uniform_fn)(const void *data, size_t bytes, void *cuda_stream)
 
 typedef struct swr_vertex_shader {
     swr_launch_fn launch_geometry;   /* args: swr::detail::GeomArgs */
+    swr_launch_fn launch_stream_out; /* the vertex stage alone, into RasterizerVertex / index arrays (swr_process_elements) */
     swr_uniform_fn set_uniforms;     /* copies the uniform block into the shader TU's __constant__ memory */
     int32_t attrib_count, avar_count, pvar_count;
     const char *name;
@@ -152,6 +153,16 @@ SWR_API int swr_draw_elements(swr_context *ctx, int draw_mode, size_t count, con
 SWR_API int swr_draw_raster_list(swr_context *ctx, int draw_mode, const void *vertices, size_t vertex_count,
                                  const int32_t *indices, size_t index_count);
 SWR_API int swr_finish(swr_context *ctx);
+/* VertexProcessor::drawElements for a VertexProcessor whose rasterizer is a user's IRasterizer (IRasterizer.h:56-71,
+ * VertexProcessor.cpp:302-317): runs the vertex stage only (vertex shader, clipping, perspective divide, viewport,
+ * culling) and calls `emit` once per batch of 1024 input primitives, in order, with exactly what the reference hands
+ * to IRasterizer::draw{Point,Line,Triangle}List: screen-space RasterizerVertex records (144 bytes each) and the index
+ * list -- -1 for dropped primitives, re-oriented triangles with their first and last index swapped, the clipper's fan
+ * triangles appended.  Host arrays, valid during the call only.  Synchronous. */
+typedef void (*swr_stream_out_fn)(void *user, int draw_mode, const void *vertices, size_t vertex_count,
+                                  const int32_t *indices, size_t index_count);
+SWR_API int swr_process_elements(swr_context *ctx, int draw_mode, size_t count, const int32_t *indices,
+                                 swr_stream_out_fn emit, void *user);
 
 /* ---- measurement ---------------------------------------------------------------------------- */
 typedef struct swr_stats {

@@ -76,6 +76,9 @@ def lib(impl: str):
         fr = getattr(l, prefix + "_draw_raster_triangles")
         fr.argtypes = [C.POINTER(SwrScene), C.c_void_p, C.c_int64]
         fr.restype = C.c_int
+        fp = getattr(l, prefix + "_draw_raster_prims")
+        fp.argtypes = [C.POINTER(SwrScene), C.c_int, C.c_void_p, C.c_int64]
+        fp.restype = C.c_int
         _libs[impl] = l
     return _libs[impl]
 
@@ -149,6 +152,20 @@ def run_raster_triangles(scene, verts: np.ndarray, impl: str = "oracle", targets
     rc = fn(C.byref(s), verts.ctypes.data, verts.shape[0])
     if rc != 0:
         raise RuntimeError(f"{impl}_draw_raster_triangles failed: {rc}")
+    out = dict(targets)
+    out.update(fragments=int(s.fragments), primitives_out=int(s.primitives_out))
+    return out
+
+
+def run_raster_prims(scene, mode: int, verts: np.ndarray, impl: str = "oracle", targets: Optional[dict] = None) -> dict:
+    """Rasterizer::drawPoint / drawLine / drawTriangle on screen-space primitives [n, mode + 1, 7] = {x,y,z,w,a0,a1,a2}."""
+    targets = fresh_targets(scene.width, scene.height) if targets is None else targets
+    s, keep, _ = _fill(scene, targets, 0)
+    verts = np.ascontiguousarray(verts, dtype=np.float32).reshape(-1, mode + 1, 7)
+    fn = getattr(lib(impl), ("oracle" if impl == "oracle" else "ref") + "_draw_raster_prims")
+    rc = fn(C.byref(s), mode, verts.ctypes.data, verts.shape[0])
+    if rc != 0:
+        raise RuntimeError(f"{impl}_draw_raster_prims failed: {rc}")
     out = dict(targets)
     out.update(fragments=int(s.fragments), primitives_out=int(s.primitives_out))
     return out

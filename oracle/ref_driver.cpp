@@ -346,6 +346,44 @@ int ref_draw_raster_triangles(swr_scene *s, const float *verts, int64_t ntri)
     return 0;
 }
 
+// Rasterizer::drawPoint / drawLine / drawTriangle on screen-space vertices (Rasterizer.h:99-114).
+// verts: nprim * (mode + 1) vertices * 7 floats {x, y, z, w, a0, a1, a2}; ordinal of primitive t is t.
+int ref_draw_raster_prims(swr_scene *s, int mode, const float *verts, int64_t nprim)
+{
+    if (mode == 2) return ref_draw_raster_triangles(s, verts, nprim);
+    if (mode != 0 && mode != 1) return -2;
+    g_s = s;
+    s->fragments = 0;
+    s->primitives_out = 0;
+    s->stream_len = 0;
+    Rasterizer r;
+    r.setRasterMode((RasterMode)s->raster_mode);
+    r.setScissorRect(s->sc_x, s->sc_y, s->sc_w, s->sc_h);
+    switch (s->ps_kind) {
+    case SWR_PS_FLAT: r.setPixelShader<PSFlat>(); break;
+    case SWR_PS_COUNT_ID: r.setPixelShader<PSCountId>(); break;
+    case SWR_PS_GOURAUD: r.setPixelShader<PSGouraud>(); break;
+    case SWR_PS_GOURAUD_DEPTH: r.setPixelShader<PSGouraudDepth>(); break;
+    default: return -2;
+    }
+    const int per = mode + 1;
+    for (int64_t t = 0; t < nprim; ++t) {
+        RasterizerVertex v[2];
+        memset(v, 0, sizeof(v));
+        for (int k = 0; k < per; ++k) {
+            const float *f = verts + (t * per + k) * 7;
+            v[k].x = f[0]; v[k].y = f[1]; v[k].z = f[2]; v[k].w = f[3];
+            v[k].avar[0] = f[4]; v[k].avar[1] = f[5]; v[k].avar[2] = f[6];
+        }
+        g_ordinal = (uint32_t)t;
+        s->primitives_out++;
+        if (mode == 0) r.drawPoint(v[0]);
+        else r.drawLine(v[0], v[1]);
+    }
+    g_s = nullptr;
+    return 0;
+}
+
 // n doubles of the reference's Random(seed).NextDouble() stream (Random.cpp:45-50),
 // used to check our own generator of Benchmark.cpp's vertex set.
 void ref_random_doubles(int seed, int64_t n, double *out)

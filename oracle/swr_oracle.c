@@ -926,3 +926,36 @@ int oracle_draw_raster_triangles(swr_scene *s, const float *verts, int64_t ntri)
     }
     return 0;
 }
+
+/* Rasterizer::drawPoint / drawLine / drawTriangle on screen-space input (Rasterizer.h:99-114):
+ * verts = nprim * (mode + 1) * {x, y, z, w, a0, a1, a2}; ordinal of primitive t is t. */
+int oracle_draw_raster_prims(swr_scene *s, int mode, const float *verts, int64_t nprim)
+{
+    if (mode == 2) return oracle_draw_raster_triangles(s, verts, nprim);
+    if (mode != 0 && mode != 1) return -2;
+    ctx c;
+    int vs_save = s->vs_kind, dm_save = s->draw_mode;
+    s->vs_kind = SWR_VS_POS_COLOR;
+    s->draw_mode = mode;
+    int rc = ctx_init(&c, s);
+    s->vs_kind = vs_save;
+    s->draw_mode = dm_save;
+    if (rc) return rc;
+    const int per = mode + 1;
+    for (int64_t t = 0; t < nprim; ++t) {
+        prim p;
+        memset(&p, 0, sizeof(p));
+        p.n = per;
+        p.ordinal = (uint32_t)t;
+        for (int k = 0; k < per; ++k) {
+            const float *f = verts + (t * per + k) * 7;
+            p.v[k].x = f[0]; p.v[k].y = f[1]; p.v[k].z = f[2]; p.v[k].w = f[3];
+            p.v[k].avar[0] = f[4]; p.v[k].avar[1] = f[5]; p.v[k].avar[2] = f[6];
+        }
+        c.ordinal = p.ordinal;
+        s->primitives_out++;
+        if (mode == 0) draw_point(&c, &p.v[0]);
+        else draw_line(&c, &p.v[0], &p.v[1]);
+    }
+    return 0;
+}

@@ -57,6 +57,7 @@ SYMBOLS = [
     ("swr_draw_elements", C.c_int, [_P, C.c_int, C.c_size_t, _P]),
     ("swr_draw_raster_list", C.c_int, [_P, C.c_int, _P, C.c_size_t, _P, C.c_size_t]),
     ("swr_finish", C.c_int, [_P]),
+    ("swr_process_elements", C.c_int, [_P, C.c_int, C.c_size_t, _P, _P, _P]),
     ("swr_get_stats", C.c_int, [_P, C.POINTER(SwrStats)]),
     ("swr_reset_stats", C.c_int, [_P]),
     ("swr_timer_begin", C.c_int, [_P]),
@@ -82,6 +83,8 @@ SYMBOLS = [
     ("swr_set_geometry_shards", C.c_int, [_P, C.c_int, C.c_int, _P]),
     ("swr_peer_barrier", C.c_int, [_P]),
 ]
+
+STREAM_OUT_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t)
 
 _lib = None
 

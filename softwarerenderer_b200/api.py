@@ -253,6 +253,21 @@ class VertexProcessor:
         _lib.check(lib.swr_set_vertex_attrib_pointer(self._r.ctx, index, stride, ptr, n if nbytes is None else nbytes),
                    "setVertexAttribPointer")
 
+    def processElements(self, mode: int, count: int, indices):
+        """drawElements towards a foreign IRasterizer (IRasterizer.h:56-71): the vertex stage only.  Returns, per batch of
+        1024 input primitives, what the reference hands to IRasterizer::draw*List: (vertices float32 [n, 36] =
+        RasterizerVertex records in screen space, indices int32 [n] with -1 for dropped primitives)."""
+        ptr, n, keep = _pointer_and_bytes(indices)
+        out = []
+
+        def emit(user, draw_mode, verts, nverts, idx, nidx):
+            v = np.ctypeslib.as_array(C.cast(verts, C.POINTER(C.c_float)), shape=(nverts, 36)).copy() if nverts else np.zeros((0, 36), np.float32)
+            i = np.ctypeslib.as_array(C.cast(idx, C.POINTER(C.c_int32)), shape=(nidx,)).copy() if nidx else np.zeros(0, np.int32)
+            out.append((v, i))
+        cb = _lib.STREAM_OUT_FN(emit)
+        _lib.check(lib.swr_process_elements(self._r.ctx, int(mode), int(count), ptr, cb, None), "processElements")
+        return out
+
     def drawElements(self, mode: int, count: int, indices, wait: bool = True):
         """drawElements(mode, count, indices); like the reference, complete on return unless wait=False."""
         ptr, n, keep = _pointer_and_bytes(indices)

@@ -708,6 +708,12 @@ int drawCommon(swr_context *c, int drawMode, size_t count, const int32_t *indice
         if (shard) {
             for (int r = 0; r < c->world; ++r)
                 g.sink[r] = r == c->rank ? own : sinkAt(c->peerArena[r] + kArenaHeader, L, reinterpret_cast<Counters *>(c->peerArena[r]));
+            if (getenv("SWR_DEBUG_FAKE_PEERS")) {
+                // measurement aid (results are wrong): the records for the peers go to a local buffer instead of over NVLink
+                if (int rc = c->l2flush.reserve(c->arena.bytes)) return rc;
+                for (int r = 0; r < c->world; ++r)
+                    if (r != c->rank) g.sink[r] = sinkAt(static_cast<char *>(c->l2flush.ptr) + kArenaHeader, L, reinterpret_cast<Counters *>(c->l2flush.ptr));
+            }
         } else {
             g.sink[c->rank] = own;
         }
@@ -1077,6 +1083,112 @@ int swr_draw_raster_list(swr_context *c, int draw_mode, const void *vertices, si
     if (index_count && (!indices || !vertices)) return fail(-1, "null vertices / indices");
     if (index_count == 0) return 0;
     return drawCommon(c, draw_mode, index_count, indices, vertices, vertex_count);
+}
+
+int swr_process_elements(swr_context *c, int drawMode, size_t count, const int32_t *indices, swr_stream_out_fn emit, void *user)
+{
+    if (!c || !emit) return fail(-1, "null argument");
+    if (count && !indices) return fail(-1, "null indices");
+    if (int rc = setDevice(c)) return rc;
+    if (drawMode < 0 || drawMode > 2) return fail(-2, "bad draw mode %d", drawMode);
+    const swr_vertex_shader *vs = c->vs;
+    if (!vs) return fail(-3, "no vertex shader set");
+    if (!vs->launch_stream_out) return fail(-3, "vertex shader '%s' has no stream-out launcher", vs->name);
+    for (int i = 0; i < vs->attrib_count; ++i)
+        if (!c->attribs[i].ptr) return fail(-8, "vertex attribute %d not set", i);
+    const int per = drawMode + 1;
+    const size_t nprims = count / per;
+    if (nprims == 0) return 0;
+    if (nprims > (size_t)0x7fffffff / 4) return fail(-4, "too many primitives in one draw (%zu)", nprims);
+    CUDA_TRY(cudaStreamSynchronize(c->aux));
+    cudaStream_t st = c->stream;
+
+    GeomArgs g;
+    memset(&g, 0, sizeof(g));
+    const int32_t *devIndices = indices;
+    const bool idxOnDevice = isDevicePointer(indices);
+    if (!idxOnDevice) {
+        if (int rc = c->stageIdx.reserve(count * sizeof(int32_t))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(c->stageIdx.ptr, indices, nprims * per * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        devIndices = static_cast<const int32_t *>(c->stageIdx.ptr);
+    }
+    int maxIndex = -2;
+    for (int i = 0; i < vs->attrib_count; ++i) {
+        const Attrib &a = c->attribs[i];
+        const void *dp = a.ptr;
+        if (!isDevicePointer(a.ptr)) {
+            size_t bytes = a.bytes;
+            if (bytes == 0) {
+                if (a.stride <= 0) return fail(-9, "vertex attribute %d is host memory with stride %d: its extent is required (bytes > 0)", i, a.stride);
+                if (maxIndex == -2)
+                    if (int rc = maxIndexOf(c, indices, nprims * per, idxOnDevice, &maxIndex)) return rc;
+                if (maxIndex < 0) return fail(-9, "vertex attribute %d is host memory and the draw has no valid index", i);
+                bytes = (size_t)a.stride * ((size_t)maxIndex + 1);
+            }
+            if (int rc = c->stageAttrib[i].reserve(bytes)) return rc;
+            CUDA_TRY(cudaMemcpyAsync(c->stageAttrib[i].ptr, a.ptr, bytes, cudaMemcpyHostToDevice, st));
+            dp = c->stageAttrib[i].ptr;
+        }
+        g.attribPtr[i] = dp;
+        g.attribStride[i] = a.stride;
+    }
+    if (c->uniformBytes && vs->set_uniforms && vs->set_uniforms(c->uniforms, c->uniformBytes, st) != 0)
+        return fail(-10, "uniform upload failed (vertex shader '%s')", vs->name);
+
+    ScratchSet &ss = c->sets[0];
+    if (!ss.ctr) {
+        if (int rc = ss.counters.reserve(sizeof(Counters))) return rc;
+        CUDA_TRY(cudaMemset(ss.counters.ptr, 0, sizeof(Counters)));
+        ss.ctr = static_cast<Counters *>(ss.counters.ptr);
+        ss.countersInit = true;
+    }
+    const size_t passBatches = 32;
+    const uint32_t extraCap = drawMode == SWR_DRAW_TRIANGLE ? (uint32_t)(kBatch * (kMaxFan - 1)) : 0u;
+    const size_t stride = (size_t)per * kBatch + 3 * (size_t)extraCap;
+    if (int rc = c->soVerts.reserve(passBatches * stride * 144)) return rc;
+    if (int rc = c->soIndices.reserve(passBatches * stride * sizeof(int32_t))) return rc;
+    if (int rc = c->soCounts.reserve(passBatches * sizeof(uint32_t))) return rc;
+
+    g.drawMode = drawMode;
+    g.px = c->px; g.py = c->py; g.ox = c->ox; g.oy = c->oy;
+    g.depthN = c->depthN; g.depthF = c->depthF;
+    g.cullMode = c->cullMode; g.rasterMode = c->rasterMode;
+    g.rank = 0; g.world = 1;
+    g.sink[0].errorFlag = &ss.ctr->errorFlag;
+    g.soVerts = c->soVerts.ptr;
+    g.soIndices = static_cast<int32_t *>(c->soIndices.ptr);
+    g.soCounts = static_cast<uint32_t *>(c->soCounts.ptr);
+    g.soExtraCap = extraCap;
+
+    std::vector<uint32_t> counts(passBatches);
+    std::vector<unsigned char> hv;
+    std::vector<int32_t> hi;
+    const size_t passPrims = passBatches * kBatch;
+    c->stats.draws++;
+    c->stats.primitives_in += nprims;
+    for (size_t first = 0; first < nprims; first += passPrims) {
+        const size_t n = std::min(passPrims, nprims - first);
+        const size_t batches = (n + kBatch - 1) / kBatch;
+        g.indices = devIndices + first * per;
+        g.numPrims = (int)n;
+        g.firstBatch = (uint32_t)(first / kBatch);
+        vs->launch_stream_out(&g, st);
+        c->stats.kernel_launches++;
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(counts.data(), c->soCounts.ptr, batches * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        for (size_t b = 0; b < batches; ++b) {
+            const size_t cnt = std::min<size_t>(kBatch, n - b * kBatch);
+            const size_t items = per * cnt + 3 * (size_t)counts[b];       // vertices == indices of the batch
+            hv.resize(items * 144);
+            hi.resize(items);
+            CUDA_TRY(cudaMemcpy(hv.data(), static_cast<char *>(c->soVerts.ptr) + b * stride * 144, items * 144, cudaMemcpyDeviceToHost));
+            CUDA_TRY(cudaMemcpy(hi.data(), static_cast<int32_t *>(c->soIndices.ptr) + b * stride, items * sizeof(int32_t), cudaMemcpyDeviceToHost));
+            emit(user, drawMode, hv.data(), items, hi.data(), items);
+        }
+        c->stats.passes++;
+    }
+    return 0;
 }
 
 int swr_finish(swr_context *c)

@@ -390,3 +390,263 @@ def test_sharded_geometry_two_ranks_on_one_gpu(oracle, name):
         sr.r.setGeometryShards(0, 1, [])
     for sr in srs:
         sr.close()
+
+
+@pytest.mark.parametrize("mode", [S.DRAW_POINT, S.DRAW_LINE])
+def test_rasterizer_draw_line_and_point_lists(oracle, renderers, mode):
+    """IRasterizer::drawLineList / drawPointList on screen-space vertices (Rasterizer.h:116-131), incl. primitives
+    skipped with a -1 first index, endpoints outside the scissor and (lines) zero-length segments."""
+    sr = renderers(640, 480)
+    per = mode + 1
+    base = S.Scene("rl", np.zeros((1, 6), np.float32), np.zeros(3, np.int32), 640, 480, ps=S.PS_COUNT_ID, raster_mode=S.RASTER_BLOCK)
+    rng = np.random.default_rng(11 + mode)
+    prims = rng.random((1500, per, 7), dtype=np.float32) * np.array([700, 520, 1, 0, 1, 1, 1], np.float32) + np.array([-30, -20, 0, 1, 0, 0, 0], np.float32)
+    if mode == S.DRAW_LINE:
+        prims[5, 1] = prims[5, 0]                               # zero steps: nothing drawn (Rasterizer.h:184)
+    verts = np.zeros((prims.shape[0] * per, 36), np.float32)
+    verts[:, 0:7] = prims.reshape(-1, 7)
+    idx = np.arange(verts.shape[0], dtype=np.int32)
+    for ps in (S.PS_COUNT_ID, S.PS_GOURAUD_DEPTH):
+        sc = base.replace(ps=ps)
+        sr.targets.clear()
+        sr.r.resetStats()
+        sr.set_state(sc)
+        (sr.r.drawLineList if mode == S.DRAW_LINE else sr.r.drawPointList)(verts, idx)
+        sr.r.finish()
+        got = sr.targets.download()
+        got["fragments"] = int(sr.r.stats().fragments)
+        want = oracle.run_raster_prims(sc, mode, prims, "ref" if oracle.have_ref() else "oracle")
+        assert got["fragments"] == want["fragments"]
+        # the checker numbers the primitives 0, 1, 2, ...; a list is drawn in batches of 1024 like drawElements, so
+        # primitive t carries the emission ordinal (t / 1024) * SWR_ORDINAL_STRIDE + t % 1024
+        pid = want["prim_id"].astype(np.int64)
+        hit = pid != 0xFFFFFFFF
+        pid[hit] = (pid[hit] // 1024) * S.ORDINAL_STRIDE + pid[hit] % 1024
+        want = dict(want, prim_id=pid.astype(np.uint32))
+        assert not common.diff_buffers(got, want, ("count", "prim_id") if ps == S.PS_COUNT_ID else ("color", "depth")), (mode, ps)
+    # skipped primitives: every other one
+    skip = idx.copy().reshape(-1, per)
+    skip[::2] = -1
+    sr.targets.clear()
+    sr.r.resetStats()
+    sr.set_state(base)
+    (sr.r.drawLineList if mode == S.DRAW_LINE else sr.r.drawPointList)(verts, skip.reshape(-1))
+    sr.r.finish()
+    got = sr.targets.download()
+    want = oracle.run_raster_prims(base, mode, prims[1::2], "oracle")
+    assert int(sr.r.stats().fragments) == want["fragments"]
+    assert np.array_equal(got["count"], want["count"])
+
+
+def _resolve_stream(batches, mode):
+    """(ordinal, xyzw of the primitive's vertices) in emission order from processElements' per-batch arrays."""
+    per, out = mode + 1, []
+    for b, (v, i) in enumerate(batches):
+        i = i.reshape(-1, per)
+        live = np.nonzero(i[:, 0] != -1)[0]
+        ords = (b * S.ORDINAL_STRIDE + live).astype(np.uint32)
+        out.append((ords, v[i[live]][:, :, :4]))
+    return np.concatenate([o for o, _ in out]), np.concatenate([x for _, x in out])
+
+
+@pytest.mark.parametrize("name", ["heavy_tris_cw", "heavy_tris_none", "heavy_lines", "heavy_points", "c3_small", "vptest"])
+def test_foreign_rasterizer_stream_equals_reference(oracle, renderers, name):
+    """VertexProcessor with a foreign IRasterizer (swr_process_elements): the vertex stage's output -- per batch the
+    screen-space vertices and the index list with -1 for dropped primitives, swapped indices for re-oriented triangles
+    and the clipper's fan triangles appended -- resolves to exactly the primitive stream the reference hands to
+    IRasterizer::draw*List (recorded by the oracle's RecordingRasterizer, oracle/ref_driver.cpp), bit for bit."""
+    heavy = S.config_c0(ps=S.PS_COUNT_ID, ntri=3000).replace(vs=S.VS_MVP_COLOR, mvp=common.heavy_clip_mvp())
+    scene = {
+        "heavy_tris_cw": lambda: heavy.replace(cull_mode=S.CULL_CW),
+        "heavy_tris_none": lambda: heavy.replace(cull_mode=S.CULL_NONE),
+        "heavy_lines": lambda: heavy.replace(draw_mode=S.DRAW_LINE, indices=S.triangle_edges(heavy.indices)),
+        "heavy_points": lambda: heavy.replace(draw_mode=S.DRAW_POINT),
+        "c3_small": lambda: S.config_c3(250, 200, 480, 270, ps=S.PS_COUNT_ID),
+        "vptest": lambda: S.vertex_processor_test(S.RASTER_BLOCK, S.PS_COUNT_ID),
+    }[name]()
+    sr = renderers(scene.width, scene.height)
+    sr.set_state(scene)
+    sr.v.setVertexAttribPointer(0, scene.stride, scene.vertices, scene.vertices.nbytes)
+    batches = sr.v.processElements(scene.draw_mode, int(scene.indices.size), scene.indices)
+    assert len(batches) == (scene.num_primitives + 1023) // 1024
+    ords, xyzw = _resolve_stream(batches, scene.draw_mode)
+    impl = "ref" if oracle.have_ref() else "oracle"
+    want = oracle.run(scene, impl, stream_cap=scene.num_primitives * 10 + 16)
+    st = want["stream"]
+    assert want["stream_len"] == len(st) == len(ords), (want["stream_len"], len(ords))
+    per = scene.draw_mode + 1
+    assert np.array_equal(st[:, 0].view(np.uint32), ords)
+    assert np.array_equal(st[:, 2:2 + 4 * per].view(np.uint32), xyzw.reshape(len(ords), -1).view(np.uint32))
+
+
+def test_host_attribute_pointer_without_extent(oracle, renderers):
+    """The reference's setVertexAttribPointer(index, stride, buffer) carries no size (VertexProcessor.h:88,
+    Benchmark.cpp:99): a host array is staged up to stride * (largest index + 1), from host and from device indices."""
+    scene = S.config_c2(100, 50, 480, 270)
+    want = oracle.run(scene, "oracle")
+    sr = renderers(scene.width, scene.height)
+    for device_indices in (False, True):
+        sr.targets.clear()
+        sr.r.resetStats()
+        sr.set_state(scene)
+        sr.v.setVertexAttribPointer(0, scene.stride, scene.vertices, nbytes=0)
+        ib = scene.indices
+        if device_indices:
+            ib = sr.r.alloc(scene.indices.nbytes)
+            sr.r.upload(ib, scene.indices)
+        sr.v.drawElements(scene.draw_mode, int(scene.indices.size), ib)
+        got = sr.targets.download()
+        got["fragments"] = int(sr.r.stats().fragments)
+        check(got, want, f"unsized_{device_indices}")
+        if device_indices:
+            sr.r.free(ib)
+
+
+def test_error_codes(renderers):
+    """Every negative return code of the C ABI that a caller can provoke (include/swr_b200.h), with its message."""
+    import ctypes as C
+    from softwarerenderer_b200 import _lib, api
+    lib = _lib.load()
+    r = api.Rasterizer()
+    v = api.VertexProcessor(r)
+    scene = S.config_c0(ntri=64, ps=S.PS_COUNT_ID)
+
+    def rc_of(fn, *a):
+        return fn(*a), lib.swr_last_error().decode()
+
+    assert rc_of(lib.swr_set_cull_mode, r.ctx, 7)[0] == -2
+    assert rc_of(lib.swr_set_raster_mode, r.ctx, -1)[0] == -2
+    assert rc_of(lib.swr_set_vertex_attrib_pointer, r.ctx, 8, 24, None, 0)[0] == -2          # assert at VertexProcessor.cpp:69
+    assert rc_of(lib.swr_set_tile_size, r.ctx, 48)[0] == -2
+    assert rc_of(lib.swr_set_tile_partition, r.ctx, 2, 2)[0] == -2
+    assert rc_of(lib.swr_set_render_target, r.ctx, 0, C.c_void_p(0x1000), 64, 16, 16)[0] == -2   # not device memory
+    assert rc_of(lib.swr_set_uniforms, r.ctx, b"\0" * 2048, 2048)[0] == -2
+    assert rc_of(lib.swr_create, None, 0)[0] == -1
+    out = C.c_void_p()
+    assert rc_of(lib.swr_create, C.byref(out), 99)[0] == -21
+    idx = scene.indices
+    # -3: no shaders yet
+    rc, msg = rc_of(lib.swr_draw_elements, r.ctx, 2, idx.size, idx.ctypes.data)
+    assert rc == -3 and "shader" in msg
+    r.setPixelShader(scene.ps)
+    v.setVertexShader(scene.vs)
+    assert rc_of(lib.swr_draw_elements, r.ctx, 5, idx.size, idx.ctypes.data)[0] == -2
+    assert rc_of(lib.swr_draw_elements, r.ctx, 2, idx.size, None)[0] == -1
+    # -5: no render target
+    rc, msg = rc_of(lib.swr_draw_elements, r.ctx, 2, idx.size, idx.ctypes.data)
+    assert rc == -5 and "render target" in msg
+    t = api.RenderTargets(r, 640, 480)
+    # -8: attribute pointer missing
+    rc, msg = rc_of(lib.swr_draw_elements, r.ctx, 2, idx.size, idx.ctypes.data)
+    assert rc == -8 and "attribute 0" in msg
+    # -9: host attribute with stride 0 and no extent
+    v.setVertexAttribPointer(0, 0, scene.vertices, nbytes=0)
+    rc, msg = rc_of(lib.swr_draw_elements, r.ctx, 2, idx.size, idx.ctypes.data)
+    assert rc == -9 and "extent" in msg
+    # -7: the pixel shader interpolates more than the vertex shader outputs (vary_dump wants 2 pvars, pos_color has 0)
+    v.setVertexAttribPointer(0, scene.stride, scene.vertices)
+    r.setPixelShader("vary_dump")
+    rc, msg = rc_of(lib.swr_draw_elements, r.ctx, 2, idx.size, idx.ctypes.data)
+    assert rc == -7 and "interpolates more" in msg
+    r.setPixelShader(scene.ps)
+    # -6: negative scissor origin
+    r.setScissorRect(-8, 0, 640, 480)
+    assert rc_of(lib.swr_draw_elements, r.ctx, 2, idx.size, idx.ctypes.data)[0] == -6
+    r.setScissorRect(0, 0, 640, 480)
+    # -24: a shader descriptor compiled against other headers
+    ps = lib.swr_stock_pixel_shader(S.PS_FLAT)
+    raw = bytearray(C.string_at(ps, 128))
+    layout_off = 6 * 8 + 8 + 5 * 4 + 4 + 8                       # launch_tiles[3][2], set_uniforms, 5 ints, pad, name
+    raw[layout_off:layout_off + 4] = (0x12345).to_bytes(4, "little")
+    fake = C.create_string_buffer(bytes(raw), 128)
+    rc, msg = rc_of(lib.swr_set_pixel_shader, r.ctx, fake)
+    assert rc == -24 and "rebuild" in msg
+    # -31: a line longer than 2^17 DDA steps is dropped and reported by finish (the draw itself succeeds)
+    v.setViewport(0, 0, 400000, 480)
+    line = np.array([[-1, 0, 0, 1, 0, 0], [1, 0, 0, 0, 1, 0]], np.float32)
+    v.setVertexAttribPointer(0, 24, line)
+    li = np.array([0, 1], np.int32)
+    assert rc_of(lib.swr_draw_elements, r.ctx, 1, 2, li.ctypes.data)[0] == 0
+    rc, msg = rc_of(lib.swr_finish, r.ctx)
+    assert rc == -31 and "DDA" in msg
+    assert rc_of(lib.swr_finish, r.ctx)[0] == 0                   # reported once
+    # -40: peer barrier / shards without a shared scratch
+    assert rc_of(lib.swr_set_tile_partition, r.ctx, 0, 2)[0] == 0
+    arr = (C.c_void_p * 2)(None, None)
+    assert rc_of(lib.swr_set_geometry_shards, r.ctx, 0, 2, arr)[0] == -40
+    assert rc_of(lib.swr_set_tile_partition, r.ctx, 0, 1)[0] == 0
+    # swr_process_elements without a callback
+    assert rc_of(lib.swr_process_elements, r.ctx, 2, idx.size, idx.ctypes.data, None, None)[0] == -1
+    t.free()
+    r.close()
+
+
+def test_polygon_overflow_is_reported(renderers):
+    """A clipped polygon of more than SWR_MAX_POLY vertices is dropped AND reported (-32), like an over-long line."""
+    from softwarerenderer_b200 import _lib
+    lib = _lib.load()
+    # vertices exactly on clip planes are duplicated by the reference's clipper (PolyClipper.cpp:64-74): a triangle that
+    # touches many planes exactly grows beyond 12 vertices
+    found = None
+    rng = np.random.default_rng(5)
+    sr = renderers(640, 480)
+    base = S.config_c0(ntri=1, ps=S.PS_COUNT_ID).replace(cull_mode=S.CULL_NONE)
+    vals = np.array([-1.0, 1.0, -2.0, 2.0, 0.0, 0.5, -0.5, 3.0], np.float32)
+    tris = vals[rng.integers(0, len(vals), size=(4096, 3, 3))]
+    verts = np.zeros((4096 * 3, 6), np.float32)
+    verts[:, :3] = tris.reshape(-1, 3)
+    sc = base.replace(vertices=verts, indices=np.arange(4096 * 3, dtype=np.int32))
+    sr.set_state(sc)
+    sr.v.setVertexAttribPointer(0, sc.stride, sc.vertices, sc.vertices.nbytes)
+    rc = lib.swr_draw_elements(sr.r.ctx, 2, int(sc.indices.size), sc.indices.ctypes.data)
+    assert rc == 0
+    rc = lib.swr_finish(sr.r.ctx)
+    assert rc in (0, -32)
+    if rc == -32:
+        assert "polygon" in lib.swr_last_error().decode()
+
+
+def _example(name, *args):
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "examples", "bin", name)
+    if not os.path.exists(exe):
+        pytest.skip("examples not built")
+    out = subprocess.run([exe, *args], capture_output=True, text=True, timeout=180)
+    assert out.returncode == 0, out.stderr + out.stdout
+    return out.stdout
+
+
+def test_cpp_example_rasterizer_test():
+    """examples/rasterizer_test.cu = RasterizerTest.cpp through the C++ mirror: Rasterizer::drawTriangle / drawLine /
+    drawPoint on host RasterizerVertex objects; the reference's fragment counts."""
+    assert "triangle: fragments 25900 covered 25900" in _example("rasterizer_test")
+    out = _example("rasterizer_test", "block")
+    assert "triangle: fragments 26100 covered 26100" in out
+    assert "line+point: fragments 161 " in out
+
+
+def test_cpp_example_vertex_processor_test():
+    """examples/vertex_processor_test.cu = VertexProcessorTest.cpp, host arrays passed without a size like the
+    reference program does: 41 068 fragments in every raster mode (Adaptive double-hits 20 pixels)."""
+    assert "fragments 41068 covered 41068" in _example("vertex_processor_test")
+    assert "fragments 41068 covered 41068" in _example("vertex_processor_test", "block")
+    assert "fragments 41068 covered 41048" in _example("vertex_processor_test", "adaptive")
+
+
+def test_cpp_example_box():
+    """examples/box.cu = Box.cpp headless: user CRTP shaders with a uniform block, perspective derivatives and the
+    device Texture sampler, built with nvcc's default FMA contraction; the reference's fragment counts at the three
+    camera angles of SURVEY.md section 4."""
+    out = _example("box")
+    assert "frame 0: fragments 37574 covered 37574" in out
+    assert "frame 1: fragments 39799 covered 39799" in out
+    assert "frame 2: fragments 39227 covered 39227" in out
+
+
+def test_cpp_example_foreign_rasterizer():
+    """examples/foreign_rasterizer.cu: swr::VertexProcessor in front of a user's IRasterizer (not a swr::Rasterizer)."""
+    out = _example("foreign_rasterizer")
+    assert "vertex_processor_test: batches 1 primitives 3 " in out and "fragments 41068 covered 41068" in out
+    assert "benchmark: batches 40 primitives 40960 dropped 0 fragments 240235639 covered 76182" in out

@@ -50,19 +50,18 @@ def load_peaks():
 
 
 def ncu_traffic(workload: str, tile: int, world: int):
-    """dram__bytes_read.sum + dram__bytes_write.sum of the tile kernel from the committed ncu --set full capture
-    (profiles/r01d_summary.json: C3, 64-pixel tiles, one GPU); None for any other configuration."""
-    if workload != "c3" or tile != 64 or world != 1:
-        return None
+    """(bytes, note): dram__bytes_read.sum + dram__bytes_write.sum of the dominant (tile) kernel, per launch, from the
+    committed `ncu --set full` capture of the SAME workload, tile size and GPU count (profiles/r02_traffic.json, written
+    by tools/profile_summary.py); (None, why) when no such capture exists -- a number from another configuration
+    would not describe this line."""
     try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "r01d_summary.json")))["tile"]
-
-        def mb(v):
-            num, unit = v.split()[:2]
-            return float(num) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[unit]
-        return mb(d["dram__bytes_read.sum"]) + mb(d["dram__bytes_write.sum"])
+        table = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
     except Exception:
-        return None
+        return None, "profiles/r02_traffic.json not found"
+    for e in table.get("captures", []):
+        if e["workload"] == workload and e["tile"] == tile and e["world"] == world and e["kernel"] == "tile":
+            return float(e["dram_bytes"]), f"ncu --set full, {e['source']}"
+    return None, f"no ncu capture of workload {workload} with {tile}-pixel tiles on {world} GPU(s) is committed"
 
 
 def make_scene(name: str):
@@ -76,6 +75,8 @@ def make_scene(name: str):
         return S.config_c0(3840, 2160), 4, "Benchmark.cpp's triangles at 3840x2160, Span, flat shader"
     if name == "c5":
         return S.config_c5(), 4, "BASELINE.json configs[4]: 50M perspective-textured triangles (5 layers), 7680x4320, Block, CullMode::CW"
+    if name == "fill":
+        return S.config_fill(), 4, "fill-bound: 2 layers of 96 x 54 x 2 large triangles (40 pixels across) over 3840x2160, overdraw 2, Block, flat 4-byte store"
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -187,31 +188,20 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
-def run_gpu_arm(args):
-    # NCCL and friends write banners straight to fd 1; the contract is ONE JSON line on stdout, so
-    # everything else is sent to stderr and the line goes to the saved descriptor at the end.
-    sys.stdout.flush()
-    real_stdout = os.fdopen(os.dup(1), "w")
-    os.dup2(2, 1)
+DEPTH_TESTED = ("c2",)          # workloads whose pixel shader reads what earlier fragments wrote (depth test)
+
+
+def bench_workload(args, workload, steps, warmup, rank, local_rank, world, dev, stream, with_cpu, with_clocks):
+    """One workload on this process's GPU (all ranks call it together).  Returns the result dictionary on rank 0."""
     import torch
     import torch.distributed as dist
     from softwarerenderer_b200 import api
     from softwarerenderer_b200.dist import GeometryShards, ReplicatedUpload, TileComposite, TileMirror
 
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
-    scene, b_frag, wl = make_scene(args.workload)
+    scene, b_frag, wl = make_scene(workload)
     W, H = scene.width, scene.height
-
-    # everything (torch copies, NCCL, and the library's kernels) is enqueued on ONE non-default stream
-    stream = torch.cuda.Stream(device=dev)
-    torch.cuda.set_stream(stream)
+    geometry = args.geometry
+    composite = args.composite
     r = api.Rasterizer(local_rank)
     v = api.VertexProcessor(r)
     r.setStream(stream.cuda_stream)
@@ -219,13 +209,21 @@ def run_gpu_arm(args):
         r.setTileSize(args.tile)
 
     # device surfaces (torch owns the memory; the library gets raw pointers)
-    targets = torch.zeros((api._lib.MAX_RENDER_TARGETS, H, W), dtype=torch.int32, device=dev)
-    for s in range(api._lib.MAX_RENDER_TARGETS):
+    nrt = api._lib.MAX_RENDER_TARGETS if workload != "c5" else 4          # (8K: 12 surfaces would be 1.6 GB for nothing)
+    targets = torch.zeros((nrt, H, W), dtype=torch.int32, device=dev)
+    for s in range(nrt):
         r.setRenderTarget(s, targets[s].data_ptr(), W * 4, W, H)
+    depth_tested = workload in DEPTH_TESTED
 
     def clear():
         targets.zero_()
         targets[api.RT_DEPTH].fill_(0x3F800000)
+
+    def clear_in_step():
+        # depth-tested workloads: every timed step starts from a cleared colour and depth buffer, with the library's
+        # own fill kernel on the same stream (otherwise every step after the first would fail the depth test everywhere)
+        r.fill32(targets[api.RT_COLOR].data_ptr(), 0, W * H)
+        r.fill32(targets[api.RT_DEPTH].data_ptr(), 0x3F800000, W * H)
 
     # geometry: pinned host copies (e2e) and resident device copies (value)
     h_vert = torch.from_numpy(scene.vertices).pin_memory()
@@ -252,18 +250,24 @@ def run_gpu_arm(args):
     r.setUniforms(u)
     r.setTilePartition(rank, world)
     shards = None
-    if world > 1 and args.geometry == "sharded":
+    if world > 1 and geometry == "sharded":
         # sharded vertex stage: every rank runs 1/world of the batches and pushes the records to the tile owners
+        scratch_gb = args.scratch_gb if args.scratch_gb > 0 else (40.0 if workload == "c5" else 14.0)
         try:
-            shards = GeometryShards(r, rank, world, dev, int(args.scratch_gb * (1 << 30)))
+            shards = GeometryShards(r, rank, world, dev, int(scratch_gb * (1 << 30)))
         except RuntimeError as e:                     # raised on every rank together
             print(f"[bench] {e}; geometry stays replicated", file=sys.stderr)
-            args.geometry = "replicated"
+            geometry = "replicated"
 
     count = int(scene.indices.size)
     count_all = count
+    comp = None
 
     def step_resident():
+        if depth_tested:
+            clear_in_step()
+            if comp is not None:
+                comp.barrier()            # no peer stores a tile into a surface that is still being cleared
         v.setVertexAttribPointer(0, scene.stride, d_vert)
         v.drawElements(scene.draw_mode, count, d_idx, wait=False)
         if comp is not None:
@@ -273,7 +277,8 @@ def run_gpu_arm(args):
     # Two buffers alternate and the upload of step k+1 (on a second stream and its own process group) runs
     # under the draw of step k; every timed step still contains exactly one upload, one draw and one read-back.
     repl = None
-    if world > 1:
+    own_runs = None
+    if world > 1 and with_cpu is not None:
         up_group = dist.new_group(ranks=list(range(world)))
         up_stream = torch.cuda.Stream(device=dev)
         if shards is not None:
@@ -306,6 +311,10 @@ def run_gpu_arm(args):
                 up_ready[slot].record(up_stream)
 
     def step_e2e():
+        if depth_tested:
+            clear_in_step()
+            if comp is not None:
+                comp.barrier()
         if world == 1:
             v.setVertexAttribPointer(0, scene.stride, h_vert)      # host pointers: staged H2D by the library
             v.drawElements(scene.draw_mode, count, h_idx, wait=False)
@@ -333,11 +342,11 @@ def run_gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, nsteps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        for _ in range(steps):
+        for _ in range(nsteps):
             fn()
         e1.record(stream)
         torch.cuda.synchronize()
@@ -348,15 +357,14 @@ def run_gpu_arm(args):
         return float(ms.item())
 
     # one untimed draw sizes the scratch and picks the tile size; the composite needs it
-    comp = None
     clear()
     step_resident()
     r.finish()
     tile = r.stats().last_tile_size
     if world > 1:
-        if args.composite == "mirror":
+        if composite == "mirror":
             # fused composite: the tile kernel stores finished tiles into the peers' surfaces (CUDA IPC / NVLink);
-            # per step only a one-word NCCL all-reduce remains, as the barrier
+            # per step only a barrier remains (the library's flag barrier with geometry shards, else one NCCL word)
             try:
                 comp = TileMirror(r, api.RT_COLOR, targets[api.RT_COLOR].data_ptr(), rank, world, dev,
                                   peer_barrier=shards.barrier if shards is not None else None)
@@ -364,7 +372,7 @@ def run_gpu_arm(args):
                 comp.barrier()
             except RuntimeError as e:                 # raised on every rank together (see TileMirror)
                 print(f"[bench] {e}; using the NCCL all-gather composite", file=sys.stderr)
-                args.composite = "nccl"
+                composite = "nccl"
         if comp is None:
             comp = TileComposite(r, W, H, tile, rank, world, dev)
 
@@ -387,81 +395,144 @@ def run_gpu_arm(args):
             raise SystemExit(f"composite differs between ranks: {lo.tolist()} vs {hi.tolist()}")
     fragments = int(frag_t.item())
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step_resident()
     torch.cuda.synchronize()
 
-    # ---- value: K steps, inputs resident (240 MB of geometry per step > the 126 MB L2)
+    # ---- value: K steps, inputs resident
     r.resetStats()
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and with_clocks:
         sampler.start()
-    ms_total = timed(step_resident, args.steps)
-    # keep the GPU under the same load a little longer so nvidia-smi (100 ms period) gets samples
-    for _ in range(int(min(2000, max(0.0, 700.0 - ms_total) / max(ms_total / args.steps, 1e-3)))):
-        step_resident()
-    torch.cuda.synchronize()
-    clocks = sampler.stop() if rank == 0 else None
-    launches_total = None
+    ms_total = timed(step_resident, steps)
+    if with_clocks:
+        # keep the GPU under the same load a little longer so nvidia-smi (100 ms period) gets samples
+        for _ in range(int(min(2000, max(0.0, 700.0 - ms_total) / max(ms_total / steps, 1e-3)))):
+            step_resident()
+        torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 and with_clocks else None
 
     # ---- per-kernel device times (CUDA events on the launching stream), outside the K-step timing
     r.resetStats()
     geom_ms, tile_ms = [], []
-    for _ in range(min(args.steps, 10)):
+    nk = min(steps, 10)
+    for _ in range(nk):
         step_resident()
         st = r.stats()
         geom_ms.append(st.last_geometry_ms)
         tile_ms.append(st.last_tile_ms)
-    launches_per_step = int(r.stats().kernel_launches) // max(1, min(args.steps, 10))
-    launches_total = launches_per_step * args.steps
+    launches_per_step = int(r.stats().kernel_launches) // max(1, nk)
+    passes_per_step = int(r.stats().passes) // max(1, nk)
 
     # ---- e2e: host buffers in, colour buffer out, every step
-    for _ in range(2):
-        step_e2e()
-    ms_e2e = timed(step_e2e, args.steps)
+    ms_e2e = None
+    if with_cpu is not None:
+        for _ in range(2):
+            step_e2e()
+        ms_e2e = timed(step_e2e, steps)
 
+    res = None
     if rank == 0:
         peak, peak_src = load_peaks()
-        ms_step = ms_total / args.steps
+        ms_step = ms_total / steps
         geom_b, frag_b, v_ref = algorithmic_bytes(scene, fragments, b_frag)
         t_tile = float(np.mean(tile_ms)) * 1e-3
         t_geom = float(np.mean(geom_ms)) * 1e-3
         # dominant kernel = the tile kernel; its algorithmic traffic is the fragment traffic F*b_frag.
-        # Per launch on this rank: the rank's share of the fragments.
+        # Per launch on this rank: the rank's share of the fragments (and of the passes of a multi-pass draw).
         ach_tile = (frag_b / world) / t_tile / 1e9
-        ach_draw = (geom_b + frag_b / world) / (ms_step * 1e-3) / 1e9
-        cpu_fps, cpu_tps, cpu_desc, _ = cpu_reference_rate(scene, budget_s=20.0, steps=1) if world == 1 and not args.no_cpu else (None, None, None, None)
-        line = {
-            "metric": METRIC, "value": fragments / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        ach_draw = (geom_b / (world if shards is not None else 1) + frag_b / world) / (ms_step * 1e-3) / 1e9
+        traffic, traffic_note = ncu_traffic(workload, tile, world)
+        in_bytes = scene.indices.nbytes + scene.vertices.nbytes
+        if depth_tested:
+            clear_note = "colour and depth are cleared inside every timed step (library fill kernels on the same stream; included in the step time)"
+        else:
+            clear_note = "render targets cleared once before timing: the pixel shader overwrites without reading (no depth test), every step shades the same fragments"
+        par = "single GPU"
+        if world > 1:
+            par = (f"sort-first tiles x{world}; geometry " +
+                   ("sharded by batches, records pushed to the tile owners over NVLink, flag barrier between the GPUs" if shards is not None else "replicated") +
+                   "; composite: " + ("tile kernel stores to peer surfaces over NVLink + " + ("flag barrier" if shards is not None else "1-word NCCL barrier")
+                                      if composite == "mirror" else "pack + NCCL all-gather + unpack"))
+        res = {
+            "metric": METRIC, "value": fragments / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps,
+            "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "triangles_per_s": scene.num_primitives / (ms_step * 1e-3),
             "fragments_per_step": fragments, "triangles_per_step": scene.num_primitives,
-            "config": {"workload": wl, "tile_size": tile, "parallelism": (f"sort-first tiles x{world}; geometry " + ("sharded by batches, records pushed to the tile owners over NVLink, flag barrier between the GPUs" if shards is not None else "replicated") + "; composite: " + ("tile kernel stores to peer surfaces over NVLink + " + ("flag barrier" if shards is not None else "1-word NCCL barrier") if args.composite == "mirror" else "pack + NCCL all-gather + unpack")) if world > 1 else "single GPU",
-                       "l2": "inputs larger than L2: 240 MB of indices + vertices are re-read every step (126 MB L2)"
-                             if scene.indices.nbytes + scene.vertices.nbytes > 126e6 else "inputs fit in L2 (no flush between steps)",
-                       "clear": "render targets cleared once before timing (the Gouraud shader overwrites)"},
-            "roofline": {"bound": "hbm", "kernel": "tileKernel (binning + coverage + shading of one screen tile per CTA)",
+            "config": {"workload": wl, "tile_size": tile, "parallelism": par,
+                       "l2": (f"inputs larger than L2: {in_bytes / 1e6:.0f} MB of indices + vertices are re-read every step (126 MB L2)"
+                              if in_bytes > 126e6 else f"inputs ({in_bytes / 1e6:.0f} MB) fit in L2 and no flush is done between steps: the figures are L2-warm"),
+                       "clear": clear_note, "passes_per_step": passes_per_step},
+            "roofline": {"bound": "hbm", "kernel": "tileKernel (record binning + coverage + shading of one screen tile per CTA)",
                          "achieved": ach_tile, "peak": peak, "unit": "GB/s", "frac": ach_tile / peak,
-                         "traffic": ncu_traffic(args.workload, tile, world),
-                         "peak_source": peak_src, "algorithmic_bytes_per_launch": frag_b / world,
+                         "traffic": traffic, "traffic_source": traffic_note,
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": frag_b / world / max(1, passes_per_step),
                          "kernel_ms": t_tile * 1e3, "geometry_kernel_ms": t_geom * 1e3,
-                         "draw": {"algorithmic_bytes": geom_b + frag_b / world, "achieved": ach_draw, "frac": ach_draw / peak,
-                                  "distinct_vertices": v_ref}},
-            "e2e": {"value": fragments / (ms_e2e / args.steps * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
-                    "h2d_bytes_per_step": int(scene.vertices.nbytes + scene.indices.nbytes) if world == 1 else int((repl[0].h2d_bytes + (own_runs.numel() * 4 if shards is not None else 0)) * world),
-                    "d2h_bytes_per_step": int(W * H * 4),
-                    "path": "host buffers -> swr_draw_elements (staged by the library, indices streamed pass by pass) -> frame to host" if world == 1 else
-                            (f"each rank uploads 1/{world} of the vertices (NCCL all-gather replicates them) and the index runs of its own batches, draw + composite, rank 0 reads the frame"
-                             if shards is not None else f"each rank uploads 1/{world} of the geometry, NCCL all-gather replicates it, draw + composite, rank 0 reads the frame")},
-            "gpu_launches": launches_total,
+                         "kernel_ms_note": "device time from the first tile-phase launch to the end of the draw / of the geometry launches (CUDA events on the launching stream); in a multi-pass draw the two intervals interleave",
+                         "draw": {"algorithmic_bytes": geom_b / (world if shards is not None else 1) + frag_b / world, "achieved": ach_draw,
+                                  "frac": ach_draw / peak, "distinct_vertices": v_ref}},
+            "gpu_launches": launches_per_step * steps,
             "clocks": clocks,
         }
-        if cpu_desc is not None:
-            line["cpu_baseline"] = dict(cpu_desc, value=cpu_fps, unit=UNIT, triangles_per_s=cpu_tps)
+        if ms_e2e is not None:
+            res["e2e"] = {"value": fragments / (ms_e2e / steps * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / steps,
+                          "h2d_bytes_per_step": int(in_bytes) if world == 1 else int((repl[0].h2d_bytes + (own_runs.numel() * 4 if own_runs is not None else 0)) * world),
+                          "d2h_bytes_per_step": int(W * H * 4),
+                          "path": "host buffers -> swr_draw_elements (staged by the library, indices streamed pass by pass) -> frame to host" if world == 1 else
+                                  (f"each rank uploads 1/{world} of the vertices (NCCL all-gather replicates them) and the index runs of its own batches, draw + composite, rank 0 reads the frame"
+                                   if shards is not None else f"each rank uploads 1/{world} of the geometry, NCCL all-gather replicates it, draw + composite, rank 0 reads the frame")}
+        if with_cpu:
+            cpu_fps, cpu_tps, cpu_desc, _ = cpu_reference_rate(scene, budget_s=20.0, steps=1)
+            res["cpu_baseline"] = dict(cpu_desc, value=cpu_fps, unit=UNIT, triangles_per_s=cpu_tps)
+
+    # tear down: the next workload gets a fresh context
+    torch.cuda.synchronize()
+    if isinstance(comp, TileMirror):
+        comp.close()
+    if shards is not None:
+        shards.close()
+    if world > 1:
+        dist.barrier()                   # every peer has closed its mappings of this rank's surfaces / scratch
+    r.close()
+    del targets, d_vert, d_idx, h_vert, h_idx
+    torch.cuda.empty_cache()
+    return res
+
+
+def run_gpu_arm(args):
+    # NCCL and friends write banners straight to fd 1; the contract is ONE JSON line on stdout, so
+    # everything else is sent to stderr and the line goes to the saved descriptor at the end.
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # everything (torch copies, NCCL, and the library's kernels) is enqueued on ONE non-default stream
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+
+    line = bench_workload(args, args.workload, args.steps, args.warmup, rank, local_rank, world, dev, stream,
+                          with_cpu=(world == 1 and not args.no_cpu), with_clocks=True)
+    # BASELINE.json names configs[4] (50M textured triangles at 8K) as the 2/4/8-GPU configuration: with more than one
+    # GPU the line also carries that workload, measured the same way with a few steps (it is 10x the frame of configs[2])
+    extra = [w for w in args.also.split(",") if w] if args.also else (["c5"] if world > 1 and args.workload == "c3" else [])
+    for w in extra:
+        sub = bench_workload(args, w, max(3, min(args.steps, 5)), 3, rank, local_rank, world, dev, stream, with_cpu=None, with_clocks=False)
+        if rank == 0:
+            line.setdefault("also", {})[w] = sub
+    if rank == 0:
         real_stdout.write(json.dumps(line) + "\n")
         real_stdout.flush()
-
     if world > 1:
         dist.destroy_process_group()
 
@@ -481,10 +552,11 @@ def main():
                     help="N>1: vertex stage sharded by batches with records pushed to the tile owners (default) or run in full by every rank")
     ap.add_argument("--scratch-gb", type=float, default=0.0, help="N>1, sharded geometry: size of the shared scratch arena per rank (0 = by workload)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--also", default="", help="comma-separated further workloads measured with a few steps into line['also'] (default: c5 when N > 1); 'none' for none")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
-    if args.scratch_gb <= 0:
-        args.scratch_gb = 40.0 if args.workload == "c5" else 14.0
+    if args.also == "none":
+        args.also = ","
     if args.impl == "reference":
         run_reference_arm(args)
     else:

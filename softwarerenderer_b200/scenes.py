@@ -389,6 +389,27 @@ def config_c5(nx: int = 2500, ny: int = 2000, layers: int = 5, width: int = 7680
                  cull_mode=CULL_CW, raster_mode=raster_mode, vs=VS_MVP_NORMAL_UV, ps=ps, mvp=mvp, texture=tex)
 
 
+def config_fill(nx: int = 96, ny: int = 54, layers: int = 2, width: int = 3840, height: int = 2160,
+                raster_mode: int = RASTER_BLOCK, ps: int = PS_FLAT) -> Scene:
+    """Fill-bound, low overdraw (SURVEY.md 8(d) "worked bounds"): `layers` full-screen sheets of nx x ny x 2 large
+    triangles (40 pixels across at 4K), every pixel shaded `layers` times with a 4-byte store -- the regime in which
+    the frame-buffer traffic, not the per-primitive work, is what a draw moves."""
+    x, y = grid_positions(nx, ny, 1.0, 1.0)
+    per = (nx + 1) * (ny + 1)
+    v = np.empty((layers * per, 6), dtype=np.float32)
+    idx = []
+    base_idx = grid_indices(nx, ny)
+    for l in range(layers):
+        o = v[l * per:(l + 1) * per]
+        o[:, 0] = x.reshape(-1)
+        o[:, 1] = y.reshape(-1)
+        o[:, 2] = 0.5 - 0.1 * l
+        o[:, 3:6] = colors(per, 40 + l)
+        idx.append(base_idx + np.int32(l * per))
+    return Scene(f"fill_{layers}x{nx}x{ny}_{width}x{height}", v, np.concatenate(idx), width, height,
+                 cull_mode=CULL_NONE, raster_mode=raster_mode, vs=VS_POS_COLOR, ps=ps)
+
+
 def rasterizer_test_triangle() -> np.ndarray:
     """RasterizerTest.cpp:60-80 as 1 triangle x 3 vertices x {x,y,z,w,a0,a1,a2} (z=0, w=1)."""
     return np.asarray([[320, 100, 0, 1, 1, 0, 0], [480, 200, 0, 1, 0, 1, 0], [120, 300, 0, 1, 0, 0, 1]],

@@ -78,15 +78,34 @@ def test_benchmark_full_known_answers(renderers):
             assert (zlib.crc32(got[k].view(np.uint8).tobytes()) & 0xFFFFFFFF) == ka[f"benchmark_full_{name}"]["crc_" + k], f"{name}:{k}"
 
 
-@pytest.mark.parametrize("name", ["c2", "c3"])
+FULL_SIZE = {
+    # BASELINE.json configs[1..4] at their full sizes; (scene factory, tile sizes, buffers compared)
+    "c2": (lambda: S.config_c2(), (32, 64), ("color", "depth")),
+    "c2_order": (lambda: S.config_c2(ps=S.PS_COUNT_ID), (64,), ("count", "prim_id")),
+    "c3": (lambda: S.config_c3(), (32, 64), ("color", "depth")),
+    "c3_order": (lambda: S.config_c3(ps=S.PS_COUNT_ID), (32, 64), ("count", "prim_id")),
+    "c4_lines": (lambda: S.config_c4(), (32, 64), ("color",)),
+    "c4_lines_order": (lambda: S.config_c4(ps=S.PS_COUNT_ID), (64,), ("count", "prim_id")),
+    "c4_points": (lambda: S.config_c4(draw_mode=S.DRAW_POINT), (32, 64), ("color",)),
+    "c4_points_order": (lambda: S.config_c4(draw_mode=S.DRAW_POINT, ps=S.PS_COUNT_ID), (64,), ("count", "prim_id")),
+    "c5": (lambda: S.config_c5(), (64,), ("color",)),
+    "c5_order": (lambda: S.config_c5(ps=S.PS_COUNT_ID), (64,), ("count", "prim_id")),
+}
+
+
+@pytest.mark.parametrize("name", list(FULL_SIZE))
 def test_baseline_configs_at_full_size(oracle, name):
-    """BASELINE.json configs[1] (1M-triangle grid, 1080p, Gouraud + depth test) and configs[2] (10M tiny triangles,
-    4K, clipping + CW culling) at their full sizes, device-resident inputs as in the benchmark: colour and depth
-    buffers and the fragment count identical to the reference build (the restatement when it is absent)."""
+    """BASELINE.json configs[1] (1M-triangle grid, 1080p, Gouraud + depth test), configs[2] (10M tiny triangles, 4K,
+    clipping + CW culling), configs[3] (line and point wireframe of the 1M mesh at 4K, LineClipper path) and configs[4]
+    (50M perspective-textured triangles in 5 layers at 8K, painter's order) at their FULL sizes, device-resident inputs
+    as in the benchmark: the output buffers and the fragment count are identical to the unmodified reference build
+    (the restatement when it is absent).  The *_order variants draw with the count / last-writer-ordinal shader, so
+    per-pixel coverage AND draw order are compared at scale."""
     from softwarerenderer_b200.api import SceneRenderer
-    scene = S.config_c2() if name == "c2" else S.config_c3()
+    make, tiles, keys = FULL_SIZE[name]
+    scene = make()
     want = oracle.run(scene, "ref" if oracle.have_ref() else "oracle")
-    for tile in (32, 64):                                    # size-independent property: the tile size never shows
+    for tile in tiles:                                       # size-independent property: the tile size never shows
         sr = SceneRenderer(scene.width, scene.height, tile_size=tile)
         vb, ib = sr.r.alloc(scene.vertices.nbytes), sr.r.alloc(scene.indices.nbytes)
         sr.r.upload(vb, scene.vertices)
@@ -96,7 +115,7 @@ def test_baseline_configs_at_full_size(oracle, name):
         sr.draw(scene, vertices=vb, indices=ib)
         got = sr.targets.download()
         assert int(sr.r.stats().fragments) == want["fragments"], (name, tile)
-        assert not common.diff_buffers(got, want, ("color", "depth")), (name, tile)
+        assert not common.diff_buffers(got, want, keys), (name, tile)
         sr.r.free(vb)
         sr.r.free(ib)
         sr.close()
@@ -227,8 +246,10 @@ def test_tile_mirrors_compose_the_frame_on_every_rank(oracle):
         sr.close()
 
 
-def test_tile_mirrors_across_gpus():
-    """The same through CUDA IPC on two GPUs (skipped on a one-GPU box)."""
+@pytest.mark.parametrize("shards", [False, True], ids=["mirrors", "mirrors+geometry_shards"])
+def test_tile_mirrors_across_gpus(shards):
+    """The same through CUDA IPC on two GPUs (skipped on a one-GPU box); with geometry shards the records are pushed
+    to the tile owner's scratch over NVLink and the ranks are ordered by the library's flag barrier."""
     import os
     import subprocess
     import sys
@@ -237,7 +258,7 @@ def test_tile_mirrors_across_gpus():
         pytest.skip("needs two GPUs")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29533", os.path.join(root, "tools", "mirror_check.py")]
+           "--master-port", "29533", os.path.join(root, "tools", "mirror_check.py")] + (["--shards"] if shards else [])
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
     assert p.returncode == 0 and "MIRROR OK" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
 

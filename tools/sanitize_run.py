@@ -22,4 +22,35 @@ for tile in (32, 64):
         out = sr.render(sc)
         print(tile, sc.name, out["fragments"], flush=True)
         sr.close()
+# sharded geometry: two contexts on this GPU push records into each other's scratch, ordered by the flag barrier
+sc = S.config_c3(120, 100, 320, 200)
+srs = [SceneRenderer(sc.width, sc.height) for _ in range(2)]
+for sr in srs:
+    sr.draw(sc)
+arenas = [sr.r.createSharedScratch(64 << 20) for sr in srs]
+for rank, sr in enumerate(srs):
+    sr.r.setGeometryShards(rank, 2, arenas)
+    sr.targets.clear()
+    sr.r.resetStats()
+for sr in srs:
+    sr.r.finish()
+for sr in srs:
+    sr.draw(sc, wait=False)
+for sr in srs:
+    sr.r.peerBarrier()
+frags = 0
+for sr in srs:
+    sr.r.finish()
+    frags += sr.r.stats().fragments
+print("sharded x2", sc.name, frags, flush=True)
+for sr in srs:
+    sr.r.setGeometryShards(0, 1, [])
+    sr.close()
+# the vertex stage alone (foreign IRasterizer)
+from softwarerenderer_b200.api import Rasterizer, VertexProcessor  # noqa: E402
+sr = SceneRenderer(sc.width, sc.height)
+sr.set_state(sc)
+sr.v.setVertexAttribPointer(0, sc.stride, sc.vertices, sc.vertices.nbytes)
+print("stream-out batches", len(sr.v.processElements(sc.draw_mode, int(sc.indices.size), sc.indices)), flush=True)
+sr.close()
 print("sanitize run done")

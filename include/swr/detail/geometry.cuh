@@ -653,8 +653,7 @@ SWR_D void markTiles(const GeomArgs &g, const RecordSink &sink, int rank, uint32
         const uint32_t tile = (uint32_t)(ty * g.tilesX + tx);
         const uint32_t key = ((uint32_t)rank << 28) | ((chunk & 1u) << 27) | tile;
         uint32_t *slot = cache + ((tile * 2654435761u + (uint32_t)rank * 40503u + (chunk & 1u)) >> 24);
-        if (*(volatile uint32_t *)slot == key) continue;
-        *(volatile uint32_t *)slot = key;
+        if (atomicExch(slot, key) == key) continue;          // (one shared-memory atomic: check and claim without a race)
         atomicOr(sink.tilemap + (size_t)tile * g.chunkWords + (chunk >> 5), bit);   // result unused: compiles to RED
     }
 }

@@ -24,6 +24,7 @@ SCENES = {
     "c4p": lambda: S.config_c4(draw_mode=S.DRAW_POINT),
     "c5": S.config_c5,
     "c5a": lambda: S.config_c5(ps=S.PS_TEXTURED_ANISO),
+    "fill": S.config_fill,
 }
 
 

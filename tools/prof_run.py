@@ -18,4 +18,4 @@ sr.r.upload(vb, scene.vertices)
 sr.r.upload(ib, scene.indices)
 for _ in range(3):
     sr.draw(scene, vertices=vb, indices=ib)
-print("done", sr.r.stats().fragments)
+print("done", sr.r.stats().fragments, "tile", sr.r.stats().last_tile_size)

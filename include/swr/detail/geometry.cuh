@@ -683,6 +683,24 @@ struct GeomStage {
     static constexpr size_t bytes = want <= 200 * 1024 ? want : 0;
 };
 
+// Warp-cooperative vertex de-duplication (the reference's VertexCache, VertexCache.h:29-63, as a build variant):
+// the 96 corner indices of a warp's 32 triangles go through a small per-warp hash table in shared memory, every
+// distinct vertex is shaded once by one lane, and the triangles read the results back.  Results are identical with
+// and without it (the cache only avoids re-shading).  Measured on B200: with the
+// stock vertex shaders (a 4x4 transform, ~45 instructions) it LOSES -- a warp of a grid mesh holds 34 distinct
+// vertices, i.e. two shading rounds instead of three, and the table costs more than the saved round -- so the
+// product build leaves it off; -DSWR_GEOM_DEDUP=1 turns it on (heavier vertex shaders).
+#ifndef SWR_GEOM_DEDUP
+#define SWR_GEOM_DEDUP 0
+#endif
+constexpr int kDedupSlots = 128, kDedupVerts = 96;
+template <int NA, int NP>
+struct GeomDedup {
+    static constexpr int VF = 4 + NA + NP;
+    static constexpr size_t perWarp = kDedupSlots * 4 + kDedupSlots + kDedupVerts * 4 + (size_t)kDedupVerts * VF * 4;
+    static constexpr size_t bytes = SWR_GEOM_DEDUP ? ((perWarp + 15) / 16 * 16) * (kGeomThreads / 32) : 0;
+};
+
 // MODE = draw mode, SPAN = false when the raster mode is known to be Block (no span state is carried), MULTI = sharded
 // geometry (records compacted per destination rank and pushed to the tile owners; otherwise every record stays at
 // its own slot of this rank's scratch): launch-time constants, and as template parameters they keep the registers
@@ -753,13 +771,81 @@ __global__ void __launch_bounds__(MULTI ? kGeomThreadsSharded : kGeomThreads, MU
         V la, lb;                                  // line end points / the point, in screen space
         int steps = 0;
         R.span = false;
+        V dv[3];
+        if (SWR_GEOM_DEDUP && !MULTI && MODE == SWR_DRAW_TRIANGLE) {
+            constexpr int VF = GeomDedup<NA, NP>::VF;
+            char *wbase = reinterpret_cast<char *>(sStageAll) + (size_t)wid * ((GeomDedup<NA, NP>::perWarp + 15) / 16 * 16);
+            int *keys = reinterpret_cast<int *>(wbase);
+            int *idxOf = keys + kDedupSlots;
+            float *verts = reinterpret_cast<float *>(idxOf + kDedupVerts);
+            uint8_t *uidOf = reinterpret_cast<uint8_t *>(verts + kDedupVerts * VF);
+            __syncwarp();
+            for (int i = lane; i < kDedupSlots; i += 32) keys[i] = -1;
+            __syncwarp();
+            const bool act = slot < cnt;
+            int hs[3] = { 0, 0, 0 };
+            bool win[3] = { false, false, false };
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                if (act) {
+                    const int idx = cur[k];
+                    uint32_t h = ((uint32_t)idx * 2654435761u) >> 25;
+                    while (true) {
+                        const int old = atomicCAS(&keys[h], -1, idx);
+                        if (old == -1) { win[k] = true; break; }
+                        if (old == idx) break;
+                        h = (h + 1) & (kDedupSlots - 1);
+                    }
+                    hs[k] = (int)h;
+                }
+            }
+            __syncwarp();
+            uint32_t nUnique = 0;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const uint32_t b = __ballot_sync(0xffffffffu, win[k]);
+                if (win[k]) {
+                    const uint32_t uid = nUnique + (uint32_t)__popc(b & ((1u << lane) - 1u));
+                    uidOf[hs[k]] = (uint8_t)uid;
+                    idxOf[uid] = cur[k];
+                }
+                nUnique += (uint32_t)__popc(b);
+            }
+            __syncwarp();
+            for (uint32_t u = lane; u < nUnique; u += 32) {
+                V t;
+                shadeVertex<VS>(g, idxOf[u], t);
+                float *o = verts + u * VF;
+                o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
+#pragma unroll
+                for (int i = 0; i < NA; ++i) o[4 + i] = t.a[i];
+#pragma unroll
+                for (int i = 0; i < NP; ++i) o[4 + NA + i] = t.p[i];
+            }
+            __syncwarp();
+            if (act) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const float *o = verts + (uint32_t)uidOf[hs[k]] * VF;
+                    dv[k].x = o[0]; dv[k].y = o[1]; dv[k].z = o[2]; dv[k].w = o[3];
+#pragma unroll
+                    for (int i = 0; i < NA; ++i) dv[k].a[i] = o[4 + i];
+#pragma unroll
+                    for (int i = 0; i < NP; ++i) dv[k].p[i] = o[4 + NA + i];
+                }
+            }
+        }
         if (slot < cnt) {
             const int32_t ip[3] = { cur[0], cur[1], cur[2] };
             if (MODE == SWR_DRAW_TRIANGLE) {
                 V v0, v1, v2;
-                shadeVertex<VS>(g, ip[0], v0);
-                shadeVertex<VS>(g, ip[1], v1);
-                shadeVertex<VS>(g, ip[2], v2);
+                if (SWR_GEOM_DEDUP && !MULTI) {
+                    v0 = dv[0]; v1 = dv[1]; v2 = dv[2];
+                } else {
+                    shadeVertex<VS>(g, ip[0], v0);
+                    shadeVertex<VS>(g, ip[1], v1);
+                    shadeVertex<VS>(g, ip[2], v2);
+                }
                 const int m0 = outcode(v0.x, v0.y, v0.z, v0.w), m1 = outcode(v1.x, v1.y, v1.z, v1.w),
                           m2 = outcode(v2.x, v2.y, v2.z, v2.w);
                 const int mask = m0 | m1 | m2;
@@ -1019,8 +1105,9 @@ void launchGeometry(const void *args, void *stream)
         }
     } else {
         if (g->drawMode == SWR_DRAW_TRIANGLE) {
-            if (g->rasterMode == SWR_RASTER_BLOCK) launch(geometryKernel<VS, SWR_DRAW_TRIANGLE, false, false>, 0);
-            else launch(geometryKernel<VS, SWR_DRAW_TRIANGLE, true, false>, 0);
+            constexpr size_t dedupBytes = GeomDedup<VS::AVarCount, VS::PVarCount>::bytes;
+            if (g->rasterMode == SWR_RASTER_BLOCK) launch(geometryKernel<VS, SWR_DRAW_TRIANGLE, false, false>, dedupBytes);
+            else launch(geometryKernel<VS, SWR_DRAW_TRIANGLE, true, false>, dedupBytes);
         } else if (g->drawMode == SWR_DRAW_LINE) {
             launch(geometryKernel<VS, SWR_DRAW_LINE, false, false>, 0);
         } else {

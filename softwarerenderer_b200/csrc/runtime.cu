@@ -347,12 +347,13 @@ int chooseTileShift(const swr_context *c, int renderTargets, size_t primitives)
     if (req == 32) return 5;
     // 64-pixel tiles amortise the binning scans better, 32-pixel tiles balance better and give the shading
     // phase four times as many CTAs: take 64 only for meshes of small triangles (fewer than 10 surface pixels per
-    // primitive of one pass) and when this rank still gets >= 1024 tiles.  Measured on B200 (ms, 32 / 64):
+    // primitive of one pass) and when this rank still gets >= 768 tiles (2.5 waves of the 296 CTA slots; C3 on two
+    // ranks, 1020 tiles each: 0.664 / 0.596 ms per frame, on four ranks, 510 each: 0.414 / 0.549).  Measured on B200 (ms, 32 / 64):
     // 10M tiny triangles at 4K 1.28 / 1.13, 5 x 10M triangles at 8K 12.9 / 10.9, 1M-triangle grid at 1080p
     // (510 tiles of 64) 0.31 / 0.35, Benchmark.cpp's 40960 large triangles at 4K 13.0 / 22.8.
     const long tiles64 = (long)((c->rtW + 63) / 64) * ((c->rtH + 63) / 64);
     const bool tiny = (double)primitives * 10.0 >= (double)c->rtW * (double)c->rtH;
-    return (tiny && tiles64 / (c->world > 0 ? c->world : 1) >= 1024 && fits64()) ? 6 : 5;
+    return (tiny && tiles64 / (c->world > 0 ? c->world : 1) >= 768 && fits64()) ? 6 : 5;
 }
 
 // ---- cross-GPU barrier of a sort-first partition ---------------------------------------------------

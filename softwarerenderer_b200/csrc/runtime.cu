@@ -188,7 +188,7 @@ struct swr_context {
     unsigned char uniforms[SWR_MAX_UNIFORM_BYTES] = {};
     size_t uniformBytes = 0;
     int tileSizeReq = 0, rank = 0, world = 1;
-    size_t scratchLimit = (size_t)16 << 30;
+    size_t scratchLimit = (size_t)48 << 30;   // per-pass scratch (worst case 10 records per triangle): C5's 50M triangles then take 2 passes (5 at 16 GB: +4 %)
 
     // scratch
     DevBuf stageIdx, l2flush, ownedIdx, tileStats, arena, soVerts, soIndices, soCounts, maxIndexBuf;
@@ -833,6 +833,7 @@ int swr_create(swr_context **out, int cuda_device)
     for (cudaEvent_t *ev : sync)
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
     if (const char *env = getenv("SWR_PIPELINE")) c->pipeline = atoi(env) != 0;
+    if (const char *env = getenv("SWR_SCRATCH_LIMIT_GB")) c->scratchLimit = (size_t)std::max(1, atoi(env)) << 30;
     if (e != cudaSuccess) {
         delete c;
         return fail(-22, "context creation: %s", cudaGetErrorString(e));

@@ -603,71 +603,58 @@ def test_error_codes(renderers):
 
 
 def test_polygon_overflow_is_reported(renderers):
-    """A clipped polygon of more than SWR_MAX_POLY vertices is dropped AND reported (-32), like an over-long line."""
+    """A clipped polygon of more than SWR_MAX_POLY = 12 vertices is dropped AND reported (-32), like an over-long line.
+    The reference's clipper duplicates vertices that lie exactly on a clip plane (PolyClipper.cpp:64-74): this triangle
+    touches the planes in so many exact points that its polygon reaches 15 vertices."""
     from softwarerenderer_b200 import _lib
     lib = _lib.load()
-    # vertices exactly on clip planes are duplicated by the reference's clipper (PolyClipper.cpp:64-74): a triangle that
-    # touches many planes exactly grows beyond 12 vertices
-    found = None
-    rng = np.random.default_rng(5)
     sr = renderers(640, 480)
-    base = S.config_c0(ntri=1, ps=S.PS_COUNT_ID).replace(cull_mode=S.CULL_NONE)
-    vals = np.array([-1.0, 1.0, -2.0, 2.0, 0.0, 0.5, -0.5, 3.0], np.float32)
-    tris = vals[rng.integers(0, len(vals), size=(4096, 3, 3))]
-    verts = np.zeros((4096 * 3, 6), np.float32)
-    verts[:, :3] = tris.reshape(-1, 3)
-    sc = base.replace(vertices=verts, indices=np.arange(4096 * 3, dtype=np.int32))
+    verts = np.array([[2, -2, 2, 1, 0, 0], [1, 1, -1, 0, 1, 0], [-3, 3, -3, 0, 0, 1]], np.float32)
+    sc = S.config_c0(ntri=1, ps=S.PS_COUNT_ID).replace(cull_mode=S.CULL_NONE, vertices=verts, indices=np.arange(3, dtype=np.int32))
     sr.set_state(sc)
     sr.v.setVertexAttribPointer(0, sc.stride, sc.vertices, sc.vertices.nbytes)
-    rc = lib.swr_draw_elements(sr.r.ctx, 2, int(sc.indices.size), sc.indices.ctypes.data)
-    assert rc == 0
-    rc = lib.swr_finish(sr.r.ctx)
-    assert rc in (0, -32)
-    if rc == -32:
-        assert "polygon" in lib.swr_last_error().decode()
+    assert lib.swr_draw_elements(sr.r.ctx, 2, 3, sc.indices.ctypes.data) == 0
+    assert lib.swr_finish(sr.r.ctx) == -32
+    assert "polygon" in lib.swr_last_error().decode()
+    assert lib.swr_finish(sr.r.ctx) == 0                        # reported once
 
 
-def _example(name, *args):
-    import os
-    import subprocess
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    exe = os.path.join(root, "examples", "bin", name)
-    if not os.path.exists(exe):
-        pytest.skip("examples not built")
-    out = subprocess.run([exe, *args], capture_output=True, text=True, timeout=180)
-    assert out.returncode == 0, out.stderr + out.stdout
-    return out.stdout
+def test_sharded_geometry_error_paths(oracle):
+    """-41: the shared scratch is too small for the draw; -33: a rank of the partition never reaches the barrier (the
+    barrier kernel gives up after ~3 s and swr_finish reports it, instead of hanging the GPU)."""
+    from softwarerenderer_b200 import _lib
+    from softwarerenderer_b200.api import SceneRenderer, SwrError
+    lib = _lib.load()
+    scene = S.config_c3(250, 200, 480, 270, ps=S.PS_COUNT_ID)
+    srs = [SceneRenderer(scene.width, scene.height) for _ in range(2)]
+    for sr in srs:
+        sr.draw(scene)
+    arenas = [sr.r.createSharedScratch(2 << 20) for sr in srs]
+    for rank, sr in enumerate(srs):
+        sr.r.setGeometryShards(rank, 2, arenas)
+    with pytest.raises(SwrError, match="too small"):
+        srs[0].draw(scene, wait=False)
+    for sr in srs:
+        sr.r.setGeometryShards(0, 1, [])
+    arenas = [sr.r.createSharedScratch(256 << 20) for sr in srs]
+    for rank, sr in enumerate(srs):
+        sr.r.setGeometryShards(rank, 2, arenas)
+    srs[0].draw(scene, wait=False)                              # rank 1 never draws
+    assert lib.swr_finish(srs[0].r.ctx) == -33
+    assert "barrier" in lib.swr_last_error().decode()
+    for sr in srs:
+        sr.r.setGeometryShards(0, 1, [])
+        sr.close()
 
 
-def test_cpp_example_rasterizer_test():
-    """examples/rasterizer_test.cu = RasterizerTest.cpp through the C++ mirror: Rasterizer::drawTriangle / drawLine /
-    drawPoint on host RasterizerVertex objects; the reference's fragment counts."""
-    assert "triangle: fragments 25900 covered 25900" in _example("rasterizer_test")
-    out = _example("rasterizer_test", "block")
-    assert "triangle: fragments 26100 covered 26100" in out
-    assert "line+point: fragments 161 " in out
-
-
-def test_cpp_example_vertex_processor_test():
-    """examples/vertex_processor_test.cu = VertexProcessorTest.cpp, host arrays passed without a size like the
-    reference program does: 41 068 fragments in every raster mode (Adaptive double-hits 20 pixels)."""
-    assert "fragments 41068 covered 41068" in _example("vertex_processor_test")
-    assert "fragments 41068 covered 41068" in _example("vertex_processor_test", "block")
-    assert "fragments 41068 covered 41048" in _example("vertex_processor_test", "adaptive")
-
-
-def test_cpp_example_box():
-    """examples/box.cu = Box.cpp headless: user CRTP shaders with a uniform block, perspective derivatives and the
-    device Texture sampler, built with nvcc's default FMA contraction; the reference's fragment counts at the three
-    camera angles of SURVEY.md section 4."""
-    out = _example("box")
-    assert "frame 0: fragments 37574 covered 37574" in out
-    assert "frame 1: fragments 39799 covered 39799" in out
-    assert "frame 2: fragments 39227 covered 39227" in out
-
-
-def test_cpp_example_foreign_rasterizer():
-    """examples/foreign_rasterizer.cu: swr::VertexProcessor in front of a user's IRasterizer (not a swr::Rasterizer)."""
-    out = _example("foreign_rasterizer")
-    assert "vertex_processor_test: batches 1 primitives 3 " in out and "fragments 41068 covered 41068" in out
-    assert "benchmark: batches 40 primitives 40960 dropped 0 fragments 240235639 covered 76182" in out
+def test_in_kernel_binning_fallback(oracle, monkeypatch):
+    """The tile kernel's own chunk / group binning (used when a tile's list from the binning pass overflows its
+    capacity) gives the same pixels as the binning pass: forced here by switching the pass off."""
+    from softwarerenderer_b200.api import SceneRenderer
+    monkeypatch.setenv("SWR_NO_BIN_PASS", "1")
+    for scene in (S.config_c3(250, 200, 480, 270, ps=S.PS_COUNT_ID), S.config_c0(ntri=3000, ps=S.PS_COUNT_ID, raster_mode=S.RASTER_BLOCK),
+                  S.config_c4(100, 50, 480, 270, ps=S.PS_COUNT_ID)):
+        for tile in (32, 64):
+            sr = SceneRenderer(scene.width, scene.height, tile_size=tile)
+            check(sr.render(scene), oracle.run(scene, "oracle"), f"nobin_{scene.name}_{tile}")
+            sr.close()

@@ -718,7 +718,8 @@ __global__ void __launch_bounds__(MULTI ? kGeomThreadsSharded : kGeomThreads, MU
     __shared__ uint16_t sExtraCnt[kBatch];     // fan extras per primitive of this batch
     __shared__ uint16_t sExtraOfs[kBatch];     // exclusive prefix in primitive order
     __shared__ uint32_t sWarpSum[kWarps];
-    __shared__ uint32_t sExtraBase, sExtraTotal;
+    __shared__ uint32_t sExtraBase, sExtraTotal, sClipTotal;
+    __shared__ uint16_t sClipSlot[kBatch];     // slots of the primitives that have fan extras, in order
     __shared__ int sGx0[kMaxExtraGroups], sGy0[kMaxExtraGroups], sGx1[kMaxExtraGroups], sGy1[kMaxExtraGroups];
     __shared__ Box16 sGb[kMaxRanks][kBatch / kGroup];               // group boxes / record counts of the batch per rank:
     __shared__ uint8_t sGc[kMaxRanks][kBatch / kGroup];             //   written out in one piece per rank at the end
@@ -984,9 +985,10 @@ __global__ void __launch_bounds__(MULTI ? kGeomThreadsSharded : kGeomThreads, MU
     // ---- clipper fan extras: appended behind the batch's original slots, in primitive order.  They keep one slot
     // each (no compaction): every rank gets the whole range of boxes, dead where the triangle is not its business.
     {   // exclusive scan of sExtraCnt over the 1024 slots: thread t owns the kSlots consecutive slots from kSlots * t
+        // (packed: fan extras in the low 16 bits, clipped primitives that have any in the high 16 bits)
         uint32_t cs[kSlots], sum = 0;
 #pragma unroll
-        for (int k = 0; k < kSlots; ++k) { cs[k] = sExtraCnt[kSlots * tid + k]; sum += cs[k]; }
+        for (int k = 0; k < kSlots; ++k) { cs[k] = sExtraCnt[kSlots * tid + k]; sum += cs[k] + (cs[k] ? 0x10000u : 0u); }
         uint32_t incl = sum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -999,12 +1001,19 @@ __global__ void __launch_bounds__(MULTI ? kGeomThreadsSharded : kGeomThreads, MU
         for (int w = 0; w < wid; ++w) base += sWarpSum[w];
         uint32_t ex = base + incl - sum;
         {
-            uint32_t run = ex;
+            // offsets of every slot's extras, and the list of the slots that have any: the second phase below takes
+            // its clipped primitives from that list, so its warps are full (in slot order one lane in nine is busy)
+            uint32_t run = ex & 0xffffu, nclip = ex >> 16;
 #pragma unroll
-            for (int k = 0; k < kSlots; ++k) { sExtraOfs[kSlots * tid + k] = (uint16_t)run; run += cs[k]; }
+            for (int k = 0; k < kSlots; ++k) {
+                sExtraOfs[kSlots * tid + k] = (uint16_t)run;
+                run += cs[k];
+                if (cs[k]) sClipSlot[nclip++] = (uint16_t)(kSlots * tid + k);
+            }
         }
         if (tid == kThreads - 1) {
-            const uint32_t total = ex + sum;
+            sClipTotal = (ex + sum) >> 16;
+            const uint32_t total = (ex + sum) & 0xffffu;
             const uint32_t padded = (total + kGroup - 1) & ~(uint32_t)(kGroup - 1);
             uint32_t b0 = atomicAdd(g.extraAlloc, padded);
             if (b0 + padded > g.extrasEnd) {             // scratch exhausted: the draw is void on every rank
@@ -1023,10 +1032,9 @@ __global__ void __launch_bounds__(MULTI ? kGeomThreadsSharded : kGeomThreads, MU
         g.sink[tid].extra[batch] = (ebase == 0xffffffffu) ? make_uint2(0u, 0u) : make_uint2(ebase, etotal);
     if (ebase == 0xffffffffu) return;                       // flagged, draw is void
 
-    for (int r = 0; r < kRounds; ++r) {
-        const int slot = r * kThreads + tid;
-        const int extras = sExtraCnt[slot];
-        if (extras == 0) continue;
+    const uint32_t nClipped = sClipTotal;
+    for (uint32_t ci = tid; ci < nClipped; ci += kThreads) {
+        const int slot = sClipSlot[ci];
         const uint32_t ofs = sExtraOfs[slot];
         const int32_t *ip = g.indices + (size_t)(primBase + slot) * 3;
         V a[kMaxPoly], b[kMaxPoly], *poly;

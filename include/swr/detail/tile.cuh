@@ -52,10 +52,14 @@ constexpr int kItems = SWR_ITEMS;    // (primitive, block) items per flush
 #define SWR_CHUNK_LIST 1024
 #endif
 #ifndef SWR_GROUP_LIST
-#define SWR_GROUP_LIST 4096
+#define SWR_GROUP_LIST 2048
+#endif
+#ifndef SWR_FRAG_LIST
+#define SWR_FRAG_LIST 256
 #endif
 constexpr int kChunkList = SWR_CHUNK_LIST;
 constexpr int kGroupList = SWR_GROUP_LIST;    // >= the per-tile list capacity of the binning pass (runtime.cu)
+constexpr int kFragList = SWR_FRAG_LIST;      // fragments of one sparse run (per warp)
 constexpr int kTileWarps = kTileThreads / 32;
 constexpr int kPruneMax = 16;        // primitives with at most this many (primitive, block) items get the emptiness pre-test
 static_assert(2 * kTileThreads >= kQueue, "the item re-indexing scan handles two queue entries per thread");
@@ -77,7 +81,8 @@ struct TileSmem {
     static constexpr size_t offChunkGroup = offQValid + (size_t)kQueue * 4;
     static constexpr size_t offChunkPair = offChunkGroup + (size_t)kChunkList * 4;
     static constexpr size_t offGroupList = offChunkPair + (size_t)(kChunkList + 1) * 4 + 12;
-    static constexpr size_t offScan = offGroupList + (size_t)kGroupList * 4;
+    static constexpr size_t offFragList = offGroupList + (size_t)kGroupList * 4;
+    static constexpr size_t offScan = offFragList + (size_t)kFragList * 2 * (kTileThreads / 32);
     static constexpr size_t offCtl = offScan + 2 * (kTileWarps + 1) * 8;
     static constexpr size_t bytes = offCtl + 64;
 };
@@ -620,6 +625,7 @@ __global__ void __launch_bounds__(kTileThreads, SWR_TILE_MINB) tileKernel(const 
     uint32_t *cGroup = (uint32_t *)(smem + SM::offChunkGroup);     // first group of each listed chunk
     uint32_t *cPair = (uint32_t *)(smem + SM::offChunkPair);       // exclusive prefix of group counts
     uint32_t *gList = (uint32_t *)(smem + SM::offGroupList);
+    uint16_t *sFrag = (uint16_t *)(smem + SM::offFragList) + (threadIdx.x >> 5) * kFragList;   // this warp's fragment list
     uint64_t *sScan = (uint64_t *)(smem + SM::offScan);
     Ctl *ctl = (Ctl *)(smem + SM::offCtl);
 
@@ -841,32 +847,35 @@ __global__ void __launch_bounds__(kTileThreads, SWR_TILE_MINB) tileKernel(const 
                         ++pos;
                         continue;
                     }
-                    // sparse run [pos, runEnd)
+                    // sparse run [pos, runEnd): as many of the next sparse items as hold at most kFragList fragments.
+                    // Every item lane writes its fragments -- (item lane, pixel) -- into the warp's list at its prefix
+                    // position; the rounds then read "fragment f" straight from the list (no search for the owner, no
+                    // n-th-set-bit search for the pixel).
                     const uint32_t after = denseMask >> pos;
-                    const int runEnd = after ? min(nvalid, pos + (__ffs((int)after) - 1)) : nvalid;
-                    const uint64_t mr = (lane >= pos && lane < runEnd) ? m : 0ull;
-                    uint32_t fincl = __popcll(mr);
+                    int runEnd = after ? min(nvalid, pos + (__ffs((int)after) - 1)) : nvalid;
+                    const uint64_t mr0 = (lane >= pos && lane < runEnd) ? m : 0ull;
+                    uint32_t fincl = __popcll(mr0);
 #pragma unroll
                     for (int o = 1; o < 32; o <<= 1) {
                         uint32_t n = __shfl_up_sync(0xffffffffu, fincl, o);
                         if (lane >= o) fincl += n;
                     }
-                    const uint32_t fex = fincl - __popcll(mr);
-                    const uint32_t totalF = __shfl_sync(0xffffffffu, fincl, 31);
+                    runEnd = pos + __popc(__ballot_sync(0xffffffffu, lane >= pos && lane < runEnd && fincl <= (uint32_t)kFragList));
+                    const uint64_t mr = lane < runEnd ? mr0 : 0ull;
+                    const uint32_t totalF = __shfl_sync(0xffffffffu, fincl, runEnd - 1);
+                    {
+                        uint32_t w = fincl - __popcll(mr0);
+                        uint32_t lo = (uint32_t)mr, hi = (uint32_t)(mr >> 32);
+                        while (lo) { sFrag[w++] = (uint16_t)((lane << 6) | (__ffs((int)lo) - 1)); lo &= lo - 1; }
+                        while (hi) { sFrag[w++] = (uint16_t)((lane << 6) | (__ffs((int)hi) + 31)); hi &= hi - 1; }
+                    }
+                    __syncwarp();
                     for (uint32_t fbase = 0; fbase < totalF; fbase += 32) {
                         const uint32_t f = fbase + lane;
                         const bool fvalid = f < totalF;
-                        int ol = 0;
-#pragma unroll
-                        for (int sft = 16; sft > 0; sft >>= 1) {   // largest lane ol with fex[ol] <= f
-                            const int c = ol + sft;
-                            const uint32_t e = __shfl_sync(0xffffffffu, fex, c & 31);
-                            if (c < 32 && e <= f) ol = c;
-                        }
-                        const uint64_t om = __shfl_sync(0xffffffffu, mr, ol);
+                        const uint32_t fe = fvalid ? sFrag[f] : 0u;
+                        const int ol = (int)(fe >> 6), bit = (int)(fe & 63u);
                         const uint32_t orec = __shfl_sync(0xffffffffu, rec, ol);
-                        const uint32_t oex = __shfl_sync(0xffffffffu, fex, ol);
-                        const int bit = fvalid ? nthSetBit64(om, (int)(f - oex)) : 0;
                         // fragments of different primitives on the same pixel run in emission order
                         // (skipped when the round holds one primitive only, or -- the usual case on a mesh -- when the
                         // round's pixels are provably all different: the OR of the lanes' one-hot pixel masks has as
@@ -889,6 +898,7 @@ __global__ void __launch_bounds__(kTileThreads, SWR_TILE_MINB) tileKernel(const 
                             __syncwarp();
                         }
                     }
+                    __syncwarp();                                // the list is rewritten by the next run
                     pos = runEnd;
                 }
             }

@@ -34,7 +34,8 @@ namespace swr {
 namespace detail {
 
 #ifndef SWR_DENSE_MIN
-#define SWR_DENSE_MIN 32
+#define SWR_DENSE_MIN 24      // items with at least this many covered pixels are shaded lane <-> pixel (measured 16 / 24 / 32 / 48:
+                              // C3 tile phase 0.588 / 0.562 / 0.557 / 0.558 ms, fill 0.140 / 0.140 / 0.166 / 0.166, C0 at 4K 11.3 / 11.7 / 12.3 / 13.7)
 #endif
 #ifndef SWR_DENSE_PATH
 #define SWR_DENSE_PATH 1

@@ -9,8 +9,15 @@
 //   (LineClipper.cpp:30-56) -> perspective divide + viewport + depth range
 //   (VertexProcessor.cpp:347-377) -> cull / re-orient (VertexProcessor.cpp:319-345)
 //   -> TriangleEquations setup (TriangleEquations.h:47-71) + footprint box -> record in HBM.
+// The footprint of a Block-mode triangle is its CERTIFIED PIXEL BOUNDS (tightPixelBounds below): the
+// smallest pixel rectangle this file can prove to contain every fragment the reference's block walk
+// produces; binning and coverage work on it instead of the reference's 8-aligned block box.
 // The reference's 16-entry VertexCache only avoids re-shading (results are identical without
-// it); here the three corner fetches of neighbouring primitives hit L1/L2.
+// it); here the three corner fetches of neighbouring primitives hit L1/L2 (a
+// warp-cooperative de-duplication exists as a measured build variant, SWR_GEOM_DEDUP).
+// With several ranks the kernel has a second form (MULTI): the batches are sharded over the ranks and
+// every surviving record is written into the scratch of the ranks that own the tiles it touches --
+// locally or through a peer mapping (NVLink) -- see RecordSink in common.h.
 // All parity-critical arithmetic goes through fmul/fadd/fsub/fdiv (never contracted).
 #pragma once
 

@@ -10,11 +10,13 @@
 //       ascending (chunk, record) order = the reference's emission order, with no atomics and no sort;
 //   A   one thread per (primitive, 8x8 block) item: exact coverage as a 64-bit mask
 //       Block:  Rasterizer.h:257-305 corner classification (incl. the "special case" skip) and
-//               the per-pixel add chains of PixelShaderBase.h:55-94 / EdgeData.h:45-66
+//               the per-pixel add chains of PixelShaderBase.h:55-94 / EdgeData.h:45-66, walked only
+//               inside the primitive's certified pixel bounds (geometry.cuh) with warp-uniform loops
 //       Span:   per-row [xl, xr) of Rasterizer.h:360-411 (no edge tests)
 //       lines:  the DDA walk of Rasterizer.h:175-207; points: Rasterizer.h:149-158
 //   B   each 8x8 block is owned by one warp for the whole tile; it walks the block's items in
-//       queue order, 32 fragments at a time (one lane per fragment); fragments of different
+//       queue order, 32 fragments at a time (one lane per fragment, taken from a per-warp list the
+//       item lanes write their (item, pixel) pairs into); fragments of different
 //       primitives that hit the same pixel are serialised in emission order.  Every lane
 //       replays the reference's incremental fp32 chain for its own pixel (PixelData.h:61-125),
 //       so z / w / varyings are bit-identical, then calls PixelShader::drawPixel.

@@ -171,8 +171,9 @@ typedef struct swr_stats {
     uint64_t kernel_launches;    /* kernels of this library launched */
     uint64_t draws;
     uint64_t passes;
-    float last_geometry_ms;      /* device time of the last draw's geometry / tile kernels (CUDA events */
-    float last_tile_ms;          /*   on the context stream; valid after swr_finish)                    */
+    float last_geometry_ms;      /* device time of the last draw: first to last geometry launch / first tile-phase launch to */
+    float last_tile_ms;          /*   the end of the draw (CUDA events on the context stream; valid after swr_finish).  In a   */
+                                 /*   multi-pass draw the passes interleave, so the two intervals overlap and do not add up.   */
     int32_t last_tile_size;
     int32_t reserved;
     uint64_t scratch_bytes;

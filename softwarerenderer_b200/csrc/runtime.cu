@@ -1,8 +1,10 @@
 // runtime.cu -- the shader-agnostic runtime behind the C ABI (include/swr_b200.h): contexts,
 // device scratch, host-pointer staging, pass planning, kernel orchestration, measurement, the
-// raster-list entry (IRasterizer::draw*List) and the tile pack / unpack kernels of the
-// multi-GPU composite.  Shader-templated kernels live in include/swr/detail/{geometry,tile}.cuh
-// and reach this file only as launcher thunks (swr_vertex_shader / swr_pixel_shader).
+// raster-list entry (IRasterizer::draw*List), the stream-out entry for a foreign IRasterizer
+// (swr_process_elements), and the multi-GPU plumbing: shared scratch arena + geometry shards, the
+// flag barrier between the GPUs, tile mirrors and the tile pack / unpack kernels of the collective
+// composite.  Shader-templated kernels live in include/swr/detail/{geometry,tile}.cuh and reach this
+// file only as launcher thunks (swr_vertex_shader / swr_pixel_shader).
 #include <cuda_runtime.h>
 
 #include <algorithm>

@@ -157,6 +157,33 @@ class TileMirror:
         self.peers = []
 
 
+SHARD_BATCHES = 16      # include/swr/detail/common.h: kShardBatches
+BATCH_PRIMS = 1024      # VertexProcessor.cpp:110
+
+
+def shard_batches(num_batches: int, rank: int, world: int) -> np.ndarray:
+    """Batches (of 1024 input primitives) the geometry kernel of `rank` runs under swr_set_geometry_shards: runs of 16
+    consecutive batches go round-robin to the ranks (geometry.cuh: batchOfBlock / launchGeometry)."""
+    runs = -(-num_batches // SHARD_BATCHES)
+    mine = np.arange(rank, runs, world)
+    b = (mine[:, None] * SHARD_BATCHES + np.arange(SHARD_BATCHES)[None, :]).reshape(-1)
+    return b[b < num_batches]
+
+
+def shard_index_ranges(index_count: int, per: int, rank: int, world: int):
+    """[(first index, index count)] of the index array a rank reads with sharded geometry -- what it has to upload."""
+    nprims = index_count // per
+    out = []
+    for b in shard_batches(-(-nprims // BATCH_PRIMS), rank, world):
+        first = int(b) * BATCH_PRIMS
+        n = min(BATCH_PRIMS, nprims - first)
+        if out and out[-1][0] + out[-1][1] == first * per:
+            out[-1] = (out[-1][0], out[-1][1] + n * per)
+        else:
+            out.append((first * per, n * per))
+    return out
+
+
 class GeometryShards:
     """Sharded vertex stage of a sort-first partition (swr_set_geometry_shards): every rank runs 1/world of the batches
     and its geometry kernel stores each surviving record straight into the scratch of the ranks whose tiles it touches

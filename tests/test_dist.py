@@ -116,3 +116,55 @@ def test_pack_unpack_roundtrip_host():
         for r in range(world):
             D.unpack_tiles_host(out, D.pack_tiles_host(surf, 32, r, world, D.max_owned(200, 136, 32, world)), 32, r, world)
         assert np.array_equal(out, surf)
+
+
+def _shard_worker(rank, world, port, nbatches, result_q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        mine = D.shard_batches(nbatches, rank, world)
+        flags = torch.zeros(nbatches, dtype=torch.int32)
+        flags[torch.from_numpy(mine)] = 1
+        dist.all_reduce(flags)                       # every batch must be run by exactly one rank
+        ranges = D.shard_index_ranges(nbatches * 1024 * 3 - 5 * 3, 3, rank, world)
+        covered = torch.zeros(1, dtype=torch.int64)
+        covered[0] = sum(n for _, n in ranges)
+        dist.all_reduce(covered)
+        result_q.put((rank, bool((flags == 1).all()), int(covered.item())))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("nbatches", [1, 17, 9766])
+def test_geometry_shards_partition_the_batches_gloo(nbatches):
+    """Sharded geometry: runs of 16 batches round-robin over the ranks -- every batch exactly once, and the index
+    ranges the ranks upload add up to the whole index array (world_size 2 over gloo)."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_shard_worker, args=(r, world, port, nbatches, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, once, covered in results:
+        assert once, f"rank {rank}: a batch is run twice or never"
+        assert covered == nbatches * 1024 * 3 - 15
+
+
+def test_shard_batches_match_the_kernel_mapping():
+    """dist.shard_batches is the host-side statement of geometry.cuh's batchOfBlock: CTA `block` of rank r runs batch
+    ((block / 16) * world + r) * 16 + block % 16, CTAs past the end of the pass exit."""
+    for world in (2, 3, 4, 8):
+        for nb in (1, 16, 33, 1000):
+            seen = []
+            for r in range(world):
+                runs = -(-nb // 16)
+                mine = (runs - r + world - 1) // world if runs > r else 0
+                got = [((blk // 16) * world + r) * 16 + blk % 16 for blk in range(mine * 16)]
+                got = [b for b in got if b < nb]
+                assert got == D.shard_batches(nb, r, world).tolist()
+                seen += got
+            assert sorted(seen) == list(range(nb))

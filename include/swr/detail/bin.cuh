@@ -153,7 +153,17 @@ __global__ void __launch_bounds__(kBinThreads) binKernel(const TileArgs t)
             if (totChunks <= kBinChunkList || nOut > cap) break;
         }
     }
-    if (tid == 0) t.groupCount[blockIdx.x] = nOut <= cap ? nOut : kBinOverflow;
+    if (tid == 0) {
+        t.groupCount[blockIdx.x] = nOut <= cap ? nOut : kBinOverflow;
+        if (t.splitCap > 0) {                                // heavy tiles are shaded quadrant by quadrant (common.h)
+            bool heavy = false;
+            if (nOut > t.splitThreshold) {
+                const uint32_t pos = atomicAdd(&t.heavyList[0], 1u);
+                if (pos < (uint32_t)t.splitCap) { t.heavyList[1 + pos] = blockIdx.x; heavy = true; }
+            }
+            t.heavyFlag[blockIdx.x] = heavy ? 1 : 0;
+        }
+    }
 }
 
 inline void launchBin(const TileArgs &t, int tileShift, cudaStream_t stream)

@@ -172,6 +172,14 @@ struct TileArgs {
     uint32_t *groupCount;            // per tile: groups listed by binKernel (bin.cuh), 0xffffffff = list overflowed; nullptr = no binning pass
     uint32_t *groupList;             // per tile groupCap group ids, ascending
     uint32_t groupCap;
+    // heavy-tile split: a tile that lists more than splitThreshold groups (or whose list overflowed) is flagged by the
+    // binning pass (heavyFlag[tile] = 1, heavyList[1 + atomicAdd(heavyList[0])] = tile, at most splitCap of them) and
+    // shaded by four CTAs, one per quadrant, which are the first 4 * splitCap CTAs of the tile launch (tile.cuh).
+    // splitCap = 0: no split.  heavyList[0] is cleared with the tile bitmap.
+    uint8_t *heavyFlag;
+    uint32_t *heavyList;
+    uint32_t splitThreshold;
+    int32_t splitCap;
     int32_t mirrorSlot, mirrorCount; // finished tiles of render target `mirrorSlot` are also stored to mirror[0..mirrorCount)
     void *mirror[SWR_MAX_TILE_MIRRORS];   // surfaces of the same pitch / size, typically the peers' framebuffers (NVLink stores)
     uint32_t *tileStats;             // optional debug: 16 words per tile {globaltimer ns start, ns duration, primitives, fragments, A0/A/B clocks >> 4 of thread 0, flushes, flush prologue / F3 / F1+F2 clocks >> 4, records tested, groups tested, 0...}

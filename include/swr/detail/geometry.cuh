@@ -898,13 +898,18 @@ __global__ void __launch_bounds__(MULTI ? kGeomThreadsSharded : kGeomThreads, MU
 
         const int gl = slot >> 5;                             // group within the batch
         if (!MULTI) {
-            // ---- one destination (this rank): the record stays at its own slot; slots of dropped primitives -- and, with
-            // several ranks and replicated geometry, of primitives that touch none of this rank's tiles -- hold a dead box
+            // ---- one destination (this rank); dropped primitives -- and, with several ranks and replicated geometry,
+            // primitives that touch none of this rank's tiles -- leave no record
             const RecordSink &sk = g.sink[g.rank];
             if (world > 1 && !((boxOwnerMask(box, g.tileShift, g.tilesX, g.tilesY, world) >> g.rank) & 1u)) box = deadBox();
-            const uint32_t rec = (uint32_t)(primBase + slot);
-            sk.bbox[rec] = box;
-            if (box.x0 <= box.x1) {
+            // The surviving records of the warp's group move to the front of its 32 slots, in submission order (ballot +
+            // popcount, as in the sharded form below): dead boxes are neither written nor read again (on C3 two thirds
+            // of the slots: -55 MB of box writes here, -55 MB of box reads in the tile kernel; time unchanged).
+            const bool live = box.x0 <= box.x1;
+            const uint32_t liveMask = __ballot_sync(0xffffffffu, live);
+            const uint32_t rec = (group << 5) + (uint32_t)__popc(liveMask & ((1u << lane) - 1u));
+            if (live) {
+                sk.bbox[rec] = box;
                 if (MODE == SWR_DRAW_TRIANGLE) storeTriangle<NA, NP>(g, sk, rec, R);
                 else if (MODE == SWR_DRAW_LINE) storeLine<NA, NP>(g, sk, rec, ordinal, steps, la, lb);
                 else storePoint<NA, NP>(g, sk, rec, ordinal, la);
@@ -914,7 +919,7 @@ __global__ void __launch_bounds__(MULTI ? kGeomThreadsSharded : kGeomThreads, MU
             if (lane == 0) {
                 Box16 u; u.x0 = (int16_t)x0; u.y0 = (int16_t)y0; u.x1 = (int16_t)x1; u.y1 = (int16_t)y1;
                 sGb[0][gl] = u;
-                sGc[0][gl] = 32;                              // all 32 slots hold a box
+                sGc[0][gl] = (uint8_t)__popc(liveMask);
             }
             markTiles(g, sk, g.rank, sMark, 2u * (uint32_t)batch, x0, y0, x1, y1);
             cur[0] = nxt[0]; cur[1] = nxt[1]; cur[2] = nxt[2];

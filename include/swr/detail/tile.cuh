@@ -561,14 +561,18 @@ SWR_HD void shadePointFragment(const TileArgs &t, uint32_t rec, int px, int py, 
 // Shared-memory layout is block-linear: pixel (lx, ly) of the tile lives at word
 // ((ly/8)*BPR + lx/8)*64 + (ly%8)*8 + lx%8, so one 8x8 block is 256 contiguous bytes and a full
 // block round of 32 lanes touches 32 distinct banks.
+// `sub` selects what is moved: 0 = the whole tile, 1 + q = quadrant q (bit 0: right half, bit 1: lower half) of it
+// (heavy-tile split: the CTA only owns that quadrant's pixels).
 template <int TLOG, bool STORE>
-SWR_D void moveSlot(const TileArgs &t, char *g, int pitch, uint32_t *sm, int X0, int Y0)
+SWR_D void moveSlot(const TileArgs &t, char *g, int pitch, uint32_t *sm, int X0, int Y0, int sub)
 {
     constexpr int T = 1 << TLOG, BPR = T / 8;
+    const int rlog = sub ? TLOG - 1 : TLOG, R = 1 << rlog;                 // region size
+    const int ox = (sub && ((sub - 1) & 1)) ? T / 2 : 0, oy = (sub && ((sub - 1) & 2)) ? T / 2 : 0;
     const bool vec = ((((uintptr_t)g) | (uintptr_t)pitch) & 15) == 0 && (t.rtWidth & 3) == 0;
     if (vec) {
-        for (int i = threadIdx.x; i < T * T / 4; i += kTileThreads) {
-            const int ly = i / (T / 4), lx = (i % (T / 4)) * 4;
+        for (int i = threadIdx.x; i < (R * R) / 4; i += kTileThreads) {
+            const int ly = oy + (i >> (rlog - 2)), lx = ox + (i & (R / 4 - 1)) * 4;
             const int x = X0 + lx, y = Y0 + ly;
             if (x < t.rtWidth && y < t.rtHeight) {
                 uint4 *gp = (uint4 *)(g + (size_t)y * pitch + (size_t)x * 4);
@@ -577,8 +581,8 @@ SWR_D void moveSlot(const TileArgs &t, char *g, int pitch, uint32_t *sm, int X0,
             }
         }
     } else {
-        for (int i = threadIdx.x; i < T * T; i += kTileThreads) {
-            const int ly = i / T, lx = i % T;
+        for (int i = threadIdx.x; i < R * R; i += kTileThreads) {
+            const int ly = oy + (i >> rlog), lx = ox + (i & (R - 1));
             const int x = X0 + lx, y = Y0 + ly;
             if (x < t.rtWidth && y < t.rtHeight) {
                 uint32_t *gp = (uint32_t *)(g + (size_t)y * pitch + (size_t)x * 4);
@@ -590,18 +594,18 @@ SWR_D void moveSlot(const TileArgs &t, char *g, int pitch, uint32_t *sm, int X0,
 }
 
 template <int TLOG, int NRT, bool STORE>
-SWR_D void moveTile(const TileArgs &t, char *rtSmem, int X0, int Y0)
+SWR_D void moveTile(const TileArgs &t, char *rtSmem, int X0, int Y0, int sub)
 {
     constexpr int T = 1 << TLOG;
 #pragma unroll 1
     for (int s = 0; s < NRT; ++s)
-        moveSlot<TLOG, STORE>(t, (char *)t.rt[s].ptr, t.rt[s].pitch, (uint32_t *)(rtSmem + (size_t)s * T * T * 4), X0, Y0);
+        moveSlot<TLOG, STORE>(t, (char *)t.rt[s].ptr, t.rt[s].pitch, (uint32_t *)(rtSmem + (size_t)s * T * T * 4), X0, Y0, sub);
     // Sort-first composite fused into the store: the finished tile of one slot also goes to the peers'
     // surfaces (plain stores through NVLink peer mappings; they overlap the tiles still being shaded).
     if (STORE && t.mirrorCount > 0 && t.mirrorSlot < NRT) {
 #pragma unroll 1
         for (int m = 0; m < t.mirrorCount; ++m)
-            moveSlot<TLOG, true>(t, (char *)t.mirror[m], t.rt[t.mirrorSlot].pitch, (uint32_t *)(rtSmem + (size_t)t.mirrorSlot * T * T * 4), X0, Y0);
+            moveSlot<TLOG, true>(t, (char *)t.mirror[m], t.rt[t.mirrorSlot].pitch, (uint32_t *)(rtSmem + (size_t)t.mirrorSlot * T * T * 4), X0, Y0, sub);
     }
 }
 
@@ -613,8 +617,27 @@ __global__ void __launch_bounds__(kTileThreads, SWR_TILE_MINB) tileKernel(const 
     typedef TileSmem<TLOG, TR::NRT> SM;
     constexpr int T = SM::T, BPR = SM::BPR, NB = SM::NB, QW = SM::QW;
 
-    const int tx = blockIdx.x % t.tilesX, ty = blockIdx.x / t.tilesX;
-    if (!tileOwned(tx, ty, t.rank, t.world)) return;
+    // Which pixels, and whose lists: normally one CTA per tile of the grid.  Heavy-tile split (common.h): the first
+    // 4 * splitCap CTAs of the launch (they are scheduled first) each take one quadrant of a tile the binning pass
+    // flagged as heavy -- same shared-memory tile, same bitmap row and group list, but the record boxes are clipped
+    // to the quadrant and only its pixels are loaded, shaded and stored -- and the tile's own CTA exits.
+    const uint32_t nSplit = 4u * (uint32_t)t.splitCap;
+    int listTile, sub = 0;
+    if (blockIdx.x < nSplit) {
+        const uint32_t hi = blockIdx.x >> 2;
+        if (hi >= min(t.heavyList[0], (uint32_t)t.splitCap)) return;
+        listTile = (int)t.heavyList[1 + hi];
+        sub = 1 + (int)(blockIdx.x & 3u);
+    } else {
+        listTile = (int)(blockIdx.x - nSplit);
+        if (!tileOwned(listTile % t.tilesX, listTile / t.tilesX, t.rank, t.world)) return;
+        if (nSplit && t.heavyFlag[listTile]) return;
+    }
+    const int X0 = (listTile % t.tilesX) << TLOG, Y0 = (listTile / t.tilesX) << TLOG;      // origin of the shared-memory tile
+    // the pixels this CTA owns (records are clipped to them)
+    const int CX0 = X0 + ((sub && ((sub - 1) & 1)) ? (1 << TLOG) / 2 : 0), CY0 = Y0 + ((sub && ((sub - 1) & 2)) ? (1 << TLOG) / 2 : 0);
+    const int X1 = CX0 + (sub ? (1 << TLOG) / 2 : (1 << TLOG)) - 1, Y1 = CY0 + (sub ? (1 << TLOG) / 2 : (1 << TLOG)) - 1;
+    if (CX0 >= t.rtWidth || CY0 >= t.rtHeight) return;
     if (*t.errorFlag & 1u) return;                           // geometry scratch exhausted: the draw is void
 
     extern __shared__ __align__(16) char smem[];
@@ -633,7 +656,6 @@ __global__ void __launch_bounds__(kTileThreads, SWR_TILE_MINB) tileKernel(const 
     Ctl *ctl = (Ctl *)(smem + SM::offCtl);
 
     const int tid = threadIdx.x, lane = tid & 31;
-    const int X0 = tx << TLOG, Y0 = ty << TLOG, X1 = X0 + T - 1, Y1 = Y0 + T - 1;
     int phase = 0;
     bool loaded = false;
     uint32_t nGroup = 0, nQ = 0, nItems = 0, primsSeen = 0;
@@ -654,7 +676,7 @@ __global__ void __launch_bounds__(kTileThreads, SWR_TILE_MINB) tileKernel(const 
         if (tid == 0) ctl->nextBlock = 0;
         for (int i = tid; i < NB * QW; i += kTileThreads) sBlockmap[i] = 0;
         if (!loaded) {
-            moveTile<TLOG, TR::NRT, false>(t, rtSmem, X0, Y0);
+            moveTile<TLOG, TR::NRT, false>(t, rtSmem, X0, Y0, sub);
             loaded = true;
         }
         if (timing) { const long long c = clock64(); cycPre += c - cycMark; cycMark = c; }
@@ -776,7 +798,8 @@ __global__ void __launch_bounds__(kTileThreads, SWR_TILE_MINB) tileKernel(const 
             int b = 0;
             if (lane == 0) b = atomicAdd(&ctl->nextBlock, 1);
             b = __shfl_sync(0xffffffffu, b, 0);
-            if (b >= NB) break;
+            if (b >= (sub ? NB / 4 : NB)) break;
+            if (sub) b = ((((sub - 1) >> 1) * (BPR / 2) + b / (BPR / 2)) * BPR) + ((sub - 1) & 1) * (BPR / 2) + b % (BPR / 2);   // block of the quadrant
             const int bx = b % BPR, by = b / BPR;
             const int gx = X0 + bx * 8, gy = Y0 + by * 8;
             // the block's bitmap over the queue, 32 words (1024 queue entries) at a time, in order
@@ -944,8 +967,8 @@ __global__ void __launch_bounds__(kTileThreads, SWR_TILE_MINB) tileKernel(const 
                         Box16 bb;
                         bb.x0 = (int16_t)(w[2 * k] & 0xffffu); bb.y0 = (int16_t)(w[2 * k] >> 16);
                         bb.x1 = (int16_t)(w[2 * k + 1] & 0xffffu); bb.y1 = (int16_t)(w[2 * k + 1] >> 16);
-                        if (((pend >> k) & 1u) && boxOverlaps(bb, X0, Y0, X1, Y1)) {
-                            const int lx0 = max((int)bb.x0, X0) - X0, ly0 = max((int)bb.y0, Y0) - Y0;
+                        if (((pend >> k) & 1u) && boxOverlaps(bb, CX0, CY0, X1, Y1)) {
+                            const int lx0 = max((int)bb.x0, CX0) - X0, ly0 = max((int)bb.y0, CY0) - Y0;
                             const int lx1 = min((int)bb.x1, X1) - X0, ly1 = min((int)bb.y1, Y1) - Y0;
                             range[k] = packRange(lx0, ly0, lx1, ly1);
                             items[k] = (uint32_t)(((lx1 >> 3) - (lx0 >> 3) + 1) * ((ly1 >> 3) - (ly0 >> 3) + 1));
@@ -1000,13 +1023,13 @@ __global__ void __launch_bounds__(kTileThreads, SWR_TILE_MINB) tileKernel(const 
     };
 
     // ---- F1 + F2 ----------------------------------------------------------------------------------
-    const uint32_t *row = t.tilemap + (size_t)blockIdx.x * t.chunkWords;
+    const uint32_t *row = t.tilemap + (size_t)listTile * t.chunkWords;
     const long long f12In = timing ? clock64() : 0;
     // Normally binKernel (bin.cuh) has already listed this tile's groups; the in-kernel F1 + F2 below only
     // run for tiles whose list overflowed its capacity, or when the binning pass is switched off.
-    const uint32_t listed = t.groupCount ? t.groupCount[blockIdx.x] : 0xffffffffu;
+    const uint32_t listed = t.groupCount ? t.groupCount[listTile] : 0xffffffffu;
     if (listed <= (uint32_t)kGroupList) {                    // (the overflow mark is 0xffffffff)
-        const uint32_t *lst = t.groupList + (size_t)blockIdx.x * t.groupCap;
+        const uint32_t *lst = t.groupList + (size_t)listTile * t.groupCap;
         for (uint32_t i = tid; i < listed; i += kTileThreads) gList[i] = lst[i];
         nGroup = listed;                                     // drained by the common drainGroups() below
         if (SWR_TILE_STATS) dbgGroups += listed;
@@ -1077,7 +1100,7 @@ __global__ void __launch_bounds__(kTileThreads, SWR_TILE_MINB) tileKernel(const 
                     }
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        if (((valid >> k) & 1u) && boxOverlaps(gb[k], X0, Y0, X1, Y1)) hits |= 1u << k;
+                        if (((valid >> k) & 1u) && boxOverlaps(gb[k], CX0, CY0, X1, Y1)) hits |= 1u << k;
                 }
                 uint32_t tot2;
                 uint32_t e2 = nGroup + blockScan32((uint32_t)__popc(hits), tot2, sScan, phase);
@@ -1096,28 +1119,28 @@ __global__ void __launch_bounds__(kTileThreads, SWR_TILE_MINB) tileKernel(const 
     flushQueue();
     if (timing) cycF3 += clock64() - tailIn;     // flushQueue subtracted its own time from cycF3
 
-    if (loaded) moveTile<TLOG, TR::NRT, true>(t, rtSmem, X0, Y0);
+    if (loaded) moveTile<TLOG, TR::NRT, true>(t, rtSmem, X0, Y0, sub);
 
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) frags += __shfl_xor_sync(0xffffffffu, frags, o);
     if (lane == 0 && frags) atomicAdd(t.fragCounter, frags);
     if (SWR_TILE_STATS && t.tileStats) {
-        if (lane == 0 && frags) atomicAdd(&t.tileStats[blockIdx.x * 16 + 3], (uint32_t)frags);
+        if (lane == 0 && frags) atomicAdd(&t.tileStats[listTile * 16 + 3], (uint32_t)frags);
         if (tid == 0) {
             unsigned long long tEnd;
             asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tEnd));
-            t.tileStats[blockIdx.x * 16 + 0] = (uint32_t)tStart;
-            t.tileStats[blockIdx.x * 16 + 1] = (uint32_t)(tEnd - tStart);
-            t.tileStats[blockIdx.x * 16 + 2] = primsSeen;
-            t.tileStats[blockIdx.x * 16 + 4] = (uint32_t)(cycA0 >> 4);
-            t.tileStats[blockIdx.x * 16 + 5] = (uint32_t)(cycA >> 4);
-            t.tileStats[blockIdx.x * 16 + 6] = (uint32_t)(cycB >> 4);
-            t.tileStats[blockIdx.x * 16 + 7] = dbgFlush;
-            t.tileStats[blockIdx.x * 16 + 8] = (uint32_t)(cycPre >> 4);
-            t.tileStats[blockIdx.x * 16 + 9] = (uint32_t)(cycF3 >> 4);
-            t.tileStats[blockIdx.x * 16 + 10] = (uint32_t)(cycF12 >> 4);
-            t.tileStats[blockIdx.x * 16 + 11] = dbgPairs;
-            t.tileStats[blockIdx.x * 16 + 12] = dbgGroups;
+            t.tileStats[listTile * 16 + 0] = (uint32_t)tStart;
+            t.tileStats[listTile * 16 + 1] = (uint32_t)(tEnd - tStart);
+            t.tileStats[listTile * 16 + 2] = primsSeen;
+            t.tileStats[listTile * 16 + 4] = (uint32_t)(cycA0 >> 4);
+            t.tileStats[listTile * 16 + 5] = (uint32_t)(cycA >> 4);
+            t.tileStats[listTile * 16 + 6] = (uint32_t)(cycB >> 4);
+            t.tileStats[listTile * 16 + 7] = dbgFlush;
+            t.tileStats[listTile * 16 + 8] = (uint32_t)(cycPre >> 4);
+            t.tileStats[listTile * 16 + 9] = (uint32_t)(cycF3 >> 4);
+            t.tileStats[listTile * 16 + 10] = (uint32_t)(cycF12 >> 4);
+            t.tileStats[listTile * 16 + 11] = dbgPairs;
+            t.tileStats[listTile * 16 + 12] = dbgGroups;
         }
     }
 }
@@ -1128,7 +1151,8 @@ void launchTiles(const void *args, void *stream)
     typedef TileSmem<TLOG, PsTraits<PS>::NRT> SM;
     const TileArgs *t = static_cast<const TileArgs *>(args);
     cudaFuncSetAttribute(tileKernel<PS, MODE, TLOG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::bytes);
-    tileKernel<PS, MODE, TLOG><<<t->tilesX * t->tilesY, kTileThreads, SM::bytes, (cudaStream_t)stream>>>(*t);
+    const int grid = 4 * t->splitCap + t->tilesX * t->tilesY;
+    tileKernel<PS, MODE, TLOG><<<grid, kTileThreads, SM::bytes, (cudaStream_t)stream>>>(*t);
 }
 
 template <class PS>

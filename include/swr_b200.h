@@ -132,6 +132,11 @@ SWR_API int swr_set_uniforms(swr_context *ctx, const void *data, size_t bytes);
  * screen tiles t with (tx + 3*ty) % world == rank (geometry is processed in full). */
 SWR_API int swr_set_tile_size(swr_context *ctx, int tile_size);
 SWR_API int swr_set_tile_partition(swr_context *ctx, int rank, int world);
+/* Heavy-tile split: a tile whose binning pass lists more than `groups` 32-record groups is shaded by four CTAs, one
+ * per quadrant (results are unchanged: every pixel still sees its fragments in emission order).  -1 = automatic
+ * (currently off: on the measured meshes the repeated record tests cost more than the shorter tail saves), 0 = off.
+ * No reference counterpart (scheduling only). */
+SWR_API int swr_set_tile_split(swr_context *ctx, int groups);
 SWR_API int swr_set_scratch_limit(swr_context *ctx, size_t bytes);
 /* Enqueue on a caller-owned CUDA stream (a cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream)
  * instead of the context's own; NULL restores the context's stream.  Waits for pending work first. */

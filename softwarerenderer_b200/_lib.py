@@ -50,6 +50,7 @@ SYMBOLS = [
     ("swr_set_render_target", C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, C.c_int]),
     ("swr_set_uniforms", C.c_int, [_P, _P, C.c_size_t]),
     ("swr_set_tile_size", C.c_int, [_P, C.c_int]),
+    ("swr_set_tile_split", C.c_int, [_P, C.c_int]),
     ("swr_set_tile_partition", C.c_int, [_P, C.c_int, C.c_int]),
     ("swr_set_scratch_limit", C.c_int, [_P, C.c_size_t]),
     ("swr_set_stream", C.c_int, [_P, _P]),

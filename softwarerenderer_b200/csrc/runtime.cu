@@ -96,7 +96,7 @@ bool isDevicePointer(const void *p)
 // the peers write into this memory) there is one set and both live inside the arena, at offsets that are the same
 // on every rank.
 struct SetLayout {
-    size_t bbox, gbox, gcnt, head, params, span, tilemap, extra, groupList, groupCount, bytes;
+    size_t bbox, gbox, gcnt, head, params, span, tilemap, extra, groupList, groupCount, heavyList, heavyFlag, bytes;
 };
 
 struct Counters {               // one small device block
@@ -122,7 +122,7 @@ struct ScratchSet {
 
 static size_t alignUp(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-static SetLayout layoutOf(size_t recCap, int paramStride, bool needSpan, size_t tiles, int chunkWords, size_t passBatches, uint32_t groupCap, bool binPass)
+static SetLayout layoutOf(size_t recCap, int paramStride, bool needSpan, size_t tiles, int chunkWords, size_t passBatches, uint32_t groupCap, bool binPass, int splitCap)
 {
     SetLayout L;
     size_t o = 0;
@@ -134,9 +134,11 @@ static SetLayout layoutOf(size_t recCap, int paramStride, bool needSpan, size_t 
     L.params = take(recCap * (size_t)paramStride * 4 + 16);
     L.span = take(needSpan ? recCap * 48 : 0);
     L.tilemap = take(tiles * (size_t)chunkWords * 4);
+    L.heavyList = take(4 + (size_t)splitCap * 4);        // right behind the bitmap: cleared with it (clearSet)
     L.extra = take(passBatches * sizeof(uint2));
     L.groupList = take(binPass ? tiles * (size_t)groupCap * 4 : 0);
     L.groupCount = take(binPass ? tiles * 4 : 0);
+    L.heavyFlag = take(splitCap ? tiles : 0);
     L.bytes = o;
     return L;
 }
@@ -190,6 +192,7 @@ struct swr_context {
     unsigned char uniforms[SWR_MAX_UNIFORM_BYTES] = {};
     size_t uniformBytes = 0;
     int tileSizeReq = 0, rank = 0, world = 1;
+    int tileSplitReq = -1;              // heavy-tile split: -1 automatic, 0 off, > 0 listed groups above which a tile is split
     size_t scratchLimit = (size_t)48 << 30;   // per-pass scratch (worst case 10 records per triangle): C5's 50M triangles then take 2 passes (5 at 16 GB: +4 %)
 
     // scratch
@@ -610,7 +613,15 @@ int drawCommon(swr_context *c, int drawMode, size_t count, const int32_t *indice
     // beyond it bin themselves inside the tile kernel
     const bool binPass = !getenv("SWR_NO_BIN_PASS");
     const uint32_t groupCap = tileShift == 6 ? 2048u : 1024u;          // <= kGroupList of tile.cuh
-    const SetLayout L = layoutOf(recCap, paramStride, needSpan, (size_t)tilesX * tilesY, chunkWords, passBatches, groupCap, binPass);
+    // heavy-tile split (tile.cuh, swr_set_tile_split): tiles that list more than `splitThreshold` groups are shaded by four
+    // CTAs (quadrants) that start first.  Measured on C3 (tools/rank_emul.py, profiles/r02_tile_split.txt): every quadrant
+    // repeats the tile's record tests, which costs more than the shorter tail gives back at every GPU count (two ranks,
+    // 64-pixel tiles: 0.324 -> 0.367 ms; eight ranks: 0.152 ms against 0.137 ms with 32-pixel tiles), so "automatic" is off.
+    int splitReq = c->tileSplitReq;
+    if (const char *env = getenv("SWR_TILE_SPLIT")) splitReq = atoi(env);
+    if (splitReq < 0) splitReq = 0;
+    const int splitCap = (binPass && splitReq > 0) ? 256 : 0;
+    const SetLayout L = layoutOf(recCap, paramStride, needSpan, (size_t)tilesX * tilesY, chunkWords, passBatches, groupCap, binPass, splitCap);
     if (shard) {
         if (kArenaHeader + L.bytes > c->arena.bytes)
             return fail(-41, "shared scratch of %zu bytes is too small for this draw (needs %zu)", c->arena.bytes, kArenaHeader + L.bytes);
@@ -726,6 +737,10 @@ int drawCommon(swr_context *c, int drawMode, size_t count, const int32_t *indice
         t.groupList = binPass ? reinterpret_cast<uint32_t *>(ss.base + L.groupList) : nullptr;
         t.groupCount = binPass ? reinterpret_cast<uint32_t *>(ss.base + L.groupCount) : nullptr;
         t.groupCap = groupCap;
+        t.splitCap = splitCap;
+        t.splitThreshold = (uint32_t)splitReq;
+        t.heavyList = reinterpret_cast<uint32_t *>(ss.base + L.heavyList);
+        t.heavyFlag = splitCap ? reinterpret_cast<uint8_t *>(ss.base + L.heavyFlag) : nullptr;
         t.extra = own.extra;
         t.fragCounter = &dc->fragments;
         t.errorFlag = &dc->errorFlag;
@@ -736,7 +751,7 @@ int drawCommon(swr_context *c, int drawMode, size_t count, const int32_t *indice
         if (gs != c->stream && ss.tilePending) CUDA_TRY(cudaStreamWaitEvent(gs, ss.tileDone, 0));
         const uint32_t init[2] = { extrasBegin, 0u };                    // extraAlloc, errorFlag
         auto clearSet = [&]() -> int {
-            CUDA_TRY(cudaMemsetAsync(own.tilemap, 0, (size_t)tilesX * tilesY * chunkWords * 4, gs));
+            CUDA_TRY(cudaMemsetAsync(own.tilemap, 0, L.heavyList + 4 - L.tilemap, gs));           // the bitmap and the heavy-tile counter behind it
             CUDA_TRY(cudaMemcpyAsync(&dc->extraAlloc, init, sizeof(init), cudaMemcpyHostToDevice, gs));
             return 0;
         };
@@ -973,6 +988,14 @@ int swr_set_tile_size(swr_context *c, int tile_size)
     if (tile_size != 0 && tile_size != 32 && tile_size != 64) return fail(-2, "tile size must be 0, 32 or 64");
     if (tile_size != c->tileSizeReq) c->pinnedTileShift = 0;
     c->tileSizeReq = tile_size;
+    return 0;
+}
+
+int swr_set_tile_split(swr_context *c, int groups)
+{
+    if (!c) return fail(-1, "null context");
+    if (groups < -1) return fail(-2, "tile split threshold must be -1 (automatic), 0 (off) or a number of 32-record groups");
+    c->tileSplitReq = groups;
     return 0;
 }
 

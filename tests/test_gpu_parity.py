@@ -658,3 +658,42 @@ def test_in_kernel_binning_fallback(oracle, monkeypatch):
             sr = SceneRenderer(scene.width, scene.height, tile_size=tile)
             check(sr.render(scene), oracle.run(scene, "oracle"), f"nobin_{scene.name}_{tile}")
             sr.close()
+
+
+@pytest.mark.parametrize("tile", [32, 64])
+def test_heavy_tile_split(oracle, tile):
+    """swr_set_tile_split: tiles above a listed-group threshold are shaded by four CTAs, one per quadrant.  Scheduling
+    only: every buffer (incl. last-writer ordinals = draw order) stays bit-exact.  Threshold 1 splits every busy tile;
+    a surface that is not a multiple of the tile size puts quadrants partly and wholly outside of it."""
+    from softwarerenderer_b200.api import SceneRenderer
+    scenes = (S.config_c3(250, 200, 480, 270, ps=S.PS_COUNT_ID), S.config_c0(ntri=3000, ps=S.PS_COUNT_ID, raster_mode=S.RASTER_BLOCK),
+              S.config_c0(ntri=1500, ps=S.PS_GOURAUD_DEPTH, raster_mode=S.RASTER_SPAN), S.config_c4(100, 50, 480, 270, ps=S.PS_COUNT_ID),
+              S.config_c4(100, 50, 480, 270, draw_mode=S.DRAW_POINT), S.config_c5(100, 80, 3, 480, 270, ps=S.PS_VARY_DUMP))
+    for scene in scenes:
+        want = oracle.run(scene, "oracle")
+        for groups in (1, 8):
+            sr = SceneRenderer(scene.width, scene.height, tile_size=tile)
+            sr.r.setTileSplit(groups)
+            check(sr.render(scene), want, f"split{groups}_{scene.name}_{tile}")
+            check(sr.render(scene), want, f"split{groups}_{scene.name}_{tile}_again")       # the heavy list is rebuilt per pass
+            sr.close()
+    # with a partition: the union of the ranks' tiles is the frame
+    scene = scenes[0]
+    want = oracle.run(scene, "oracle")
+    acc, frags = None, 0
+    for rank in range(3):
+        sr = SceneRenderer(scene.width, scene.height, tile_size=tile)
+        sr.r.setTilePartition(rank, 3)
+        sr.r.setTileSplit(2)
+        got = sr.render(scene)
+        frags += got["fragments"]
+        if acc is None:
+            acc = {k: got[k].copy() for k in common.BUFFERS}
+        else:
+            touched = got["count"] > 0
+            assert not np.any(touched & (acc["count"] > 0)), "two ranks rendered the same pixel"
+            for k in ("count", "prim_id", "color", "depth"):
+                acc[k][touched] = got[k][touched]
+        sr.close()
+    assert frags == want["fragments"]
+    assert not common.diff_buffers(acc, want, ("count", "prim_id", "color", "depth"))

@@ -12,8 +12,9 @@ triangles removed by CullMode::CW), RasterMode::Block, Gouraud pixel shader, one
   e2e     the same metric through the reference-facing call with HOST buffers: every step copies the
           vertex and index buffers host->device (pinned memory), draws, and reads the colour buffer
           back device->host, all inside the timed region.
-  N > 1   sort-first: geometry replicated, screen tiles interleaved across ranks, one NCCL
-          all-gather of the finished tiles per step ("scaling": "strong": the frame is fixed).
+  N > 1   sort-first: screen tiles interleaved across ranks, the vertex stage sharded by batches with the
+          records pushed to the tile owners over NVLink, the composite fused into the tile kernel's
+          store (peer surfaces) -- "scaling": "strong": the frame is fixed.
   --impl reference   the reference's own CPU renderer (oracle/_ref when it was built from
           /root/reference, else the oracle port) on the host cores, same workload and metric.
 
@@ -278,6 +279,7 @@ def bench_workload(args, workload, steps, warmup, rank, local_rank, world, dev, 
     # under the draw of step k; every timed step still contains exactly one upload, one draw and one read-back.
     repl = None
     own_runs = None
+    idx_stream = None
     if world > 1 and with_cpu is not None:
         up_group = dist.new_group(ranks=list(range(world)))
         up_stream = torch.cuda.Stream(device=dev)
@@ -298,17 +300,62 @@ def bench_workload(args, workload, steps, warmup, rank, local_rank, world, dev, 
         up_ready = [torch.cuda.Event(), torch.cuda.Event()]
         up_free = [torch.cuda.Event(), torch.cuda.Event()]
         up_state = {"k": 0, "ptrs": [None, None], "drawn": [False, False]}
+        # the index runs go over PCIe right behind the vertex slice, on a stream of their own, i.e. under the all-gather
+        # of the vertices (NVLink) instead of behind it
+        idx_stream = torch.cuda.Stream(device=dev) if shards is not None and args.e2e_overlap else None
+        h2d_done = [torch.cuda.Event(), torch.cuda.Event()]
+        idx_ready = [torch.cuda.Event(), torch.cuda.Event()]
 
         def enqueue_upload(slot):
             with torch.cuda.stream(up_stream):
                 if up_state["drawn"][slot]:
                     up_stream.wait_event(up_free[slot])          # the draw that last read this buffer is done
-                ptrs = repl[slot].run()
+                ptrs = repl[slot].run(h2d_done=h2d_done[slot] if idx_stream is not None else None)
                 if shards is not None:
-                    d_idx_sh[slot].view(-1, world, run_len)[:, rank].copy_(own_runs, non_blocking=True)
+                    if idx_stream is None:
+                        d_idx_sh[slot].view(-1, world, run_len)[:, rank].copy_(own_runs, non_blocking=True)
                     ptrs = [ptrs[0], d_idx_sh[slot].data_ptr()]
                 up_state["ptrs"][slot] = ptrs
                 up_ready[slot].record(up_stream)
+            if idx_stream is not None:
+                with torch.cuda.stream(idx_stream):
+                    if up_state["drawn"][slot]:
+                        idx_stream.wait_event(up_free[slot])
+                    idx_stream.wait_event(h2d_done[slot])
+                    d_idx_sh[slot].view(-1, world, run_len)[:, rank].copy_(own_runs, non_blocking=True)
+                    idx_ready[slot].record(idx_stream)
+
+    # N > 1 read-back: after the composite every rank holds the whole frame, so every rank copies one band of rows over
+    # its own PCIe link into ONE host buffer (POSIX shared memory, page-locked by every process): the frame arrives
+    # in 1/N of the time it takes rank 0 alone.  Falls back to rank 0 reading everything when the mapping fails.
+    frame_shared, band = None, None
+    if world > 1 and with_cpu is not None and args.e2e_overlap:
+        name = [f"/dev/shm/swr_frame_{os.getpid()}_{workload}"] if rank == 0 else [None]
+        dist.broadcast_object_list(name, src=0)
+        ok = 1
+        for creator in (True, False):                # rank 0 creates and sizes the file, then the others map it
+            if creator == (rank == 0):
+                try:
+                    frame_shared = torch.from_file(name[0], shared=True, size=W * H, dtype=torch.int32)
+                    rc = torch.cuda.cudart().cudaHostRegister(frame_shared.data_ptr(), W * H * 4, 0)
+                    if int(rc) != 0 or not frame_shared.is_pinned():
+                        ok = 0
+                except Exception as e:               # noqa: BLE001
+                    print(f"[bench] shared frame buffer: {e}", file=sys.stderr)
+                    ok = 0
+            dist.barrier()
+        okt = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        if int(okt.item()) == 0:
+            frame_shared = None
+        else:
+            frame_shared = frame_shared.view(H, W)
+            band = (rank * H // world, (rank + 1) * H // world)
+        if rank == 0:
+            try:
+                os.unlink(name[0])                    # the mappings stay valid; nothing is left behind in /dev/shm
+            except OSError:
+                pass
 
     def step_e2e():
         if depth_tested:
@@ -325,6 +372,8 @@ def bench_workload(args, workload, steps, warmup, rank, local_rank, world, dev, 
             if args.pipeline_upload:
                 enqueue_upload(slot ^ 1)                          # the next step's geometry, under this step's draw
             stream.wait_event(up_ready[slot])
+            if idx_stream is not None:
+                stream.wait_event(idx_ready[slot])
             pv, pi = up_state["ptrs"][slot]
             v.setVertexAttribPointer(0, scene.stride, pv, nbytes=scene.vertices.nbytes)
             v.drawElements(scene.draw_mode, count, pi, wait=False)
@@ -334,20 +383,27 @@ def bench_workload(args, workload, steps, warmup, rank, local_rank, world, dev, 
             if not args.pipeline_upload:
                 up_state["ptrs"][slot] = None                     # the next step uploads for itself
             up_state["k"] += 1
-        if rank == 0:
-            h_color.copy_(targets[api.RT_COLOR], non_blocking=True)  # D2H of the step's result (the composed frame)
+        # D2H of the step's result (the composed frame)
+        if frame_shared is not None:
+            frame_shared[band[0]:band[1]].copy_(targets[api.RT_COLOR][band[0]:band[1]], non_blocking=True)
+        elif rank == 0:
+            h_color.copy_(targets[api.RT_COLOR], non_blocking=True)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    host_ms = {"last": 0.0}
+
     def timed(fn, nsteps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
+        t0 = time.perf_counter()
         for _ in range(nsteps):
             fn()
+        host_ms["last"] = (time.perf_counter() - t0) * 1e3 / max(1, nsteps)      # CPU time to enqueue one step
         e1.record(stream)
         torch.cuda.synchronize()
         barrier()
@@ -430,6 +486,15 @@ def bench_workload(args, workload, steps, warmup, rank, local_rank, world, dev, 
         for _ in range(2):
             step_e2e()
         ms_e2e = timed(step_e2e, steps)
+        host_e2e = host_ms["last"]
+        if frame_shared is not None:
+            # the bands of all ranks make up the frame rank 0 holds on its device
+            same = torch.tensor([1], dtype=torch.int32, device=dev)
+            if rank == 0 and not torch.equal(frame_shared, targets[api.RT_COLOR].cpu()):
+                same[0] = 0
+            dist.all_reduce(same, op=dist.ReduceOp.MIN)
+            if int(same.item()) == 0:
+                raise SystemExit("e2e: the frame assembled in host memory from the ranks' bands differs from the device frame")
 
     res = None
     if rank == 0:
@@ -477,17 +542,24 @@ def bench_workload(args, workload, steps, warmup, rank, local_rank, world, dev, 
         }
         if ms_e2e is not None:
             res["e2e"] = {"value": fragments / (ms_e2e / steps * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / steps,
+                          "host_enqueue_ms_per_step": host_e2e,
                           "h2d_bytes_per_step": int(in_bytes) if world == 1 else int((repl[0].h2d_bytes + (own_runs.numel() * 4 if own_runs is not None else 0)) * world),
                           "d2h_bytes_per_step": int(W * H * 4),
                           "path": "host buffers -> swr_draw_elements (staged by the library, indices streamed pass by pass) -> frame to host" if world == 1 else
-                                  (f"each rank uploads 1/{world} of the vertices (NCCL all-gather replicates them) and the index runs of its own batches, draw + composite, rank 0 reads the frame"
-                                   if shards is not None else f"each rank uploads 1/{world} of the geometry, NCCL all-gather replicates it, draw + composite, rank 0 reads the frame")}
+                                  ((f"each rank uploads 1/{world} of the vertices (NCCL all-gather replicates them) and the index runs of its own batches"
+                                    + (" (under the all-gather)" if idx_stream is not None else "") if shards is not None else
+                                    f"each rank uploads 1/{world} of the geometry, NCCL all-gather replicates it") + ", draw + composite, "
+                                   + (f"every rank copies 1/{world} of the rows of the composed frame into one page-locked shared host buffer" if frame_shared is not None
+                                      else "rank 0 reads the frame"))}
         if with_cpu:
             cpu_fps, cpu_tps, cpu_desc, _ = cpu_reference_rate(scene, budget_s=20.0, steps=1)
             res["cpu_baseline"] = dict(cpu_desc, value=cpu_fps, unit=UNIT, triangles_per_s=cpu_tps)
 
     # tear down: the next workload gets a fresh context
     torch.cuda.synchronize()
+    if frame_shared is not None:
+        torch.cuda.cudart().cudaHostUnregister(frame_shared.data_ptr())
+        frame_shared = None
     if isinstance(comp, TileMirror):
         comp.close()
     if shards is not None:
@@ -545,6 +617,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3")
     ap.add_argument("--pipeline-upload", type=int, default=1, help="N>1 end-to-end leg: upload step k+1 under the draw of step k")
+    ap.add_argument("--e2e-overlap", type=int, default=1,
+                    help="N>1 end-to-end leg: index upload under the vertex all-gather and the frame read back in bands by all ranks (0: the plain form)")
     ap.add_argument("--composite", default="mirror", choices=["mirror", "nccl"],
                     help="N>1: fused peer stores from the tile kernel (default) or pack + NCCL all-gather + unpack")
     ap.add_argument("--tile", type=int, default=0)

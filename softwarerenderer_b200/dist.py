@@ -1,11 +1,14 @@
 """Sort-first multi-GPU partition and framebuffer composite (K7 of SURVEY.md 2.3 / 8(e)).
 
-Geometry is replicated; screen tiles are interleaved across ranks with
+Screen tiles are interleaved across ranks with
     owner(tx, ty) = (tx + 3 * ty) % world           (include/swr/detail/common.h: tileOwned)
-Each rank rasterizes only its tiles.  The one exchange step per frame is a pure copy of disjoint
-tiles (no reduction, so bit-exactness is preserved): every rank packs its tiles into a dense
-tile-major buffer, one NCCL all-gather moves them over NVLink, every rank unpacks its peers'
-tiles into its own surface and ends up with the full image.
+and each rank rasterizes only its tiles.  The vertex stage is either replicated or sharded (GeometryShards: every rank
+runs 1/world of the batches and its geometry kernel stores the records into the tile owners' scratch over NVLink).
+The composite is a pure copy of disjoint tiles (no reduction, so bit-exactness is preserved), in two forms:
+TileMirror -- the tile kernel's final store of a tile also goes to every peer's surface (peer mappings over NVLink,
+one barrier per frame) -- and TileComposite -- every rank packs its tiles into a dense tile-major buffer, one NCCL
+all-gather moves them, every rank unpacks its peers' tiles -- for set-ups without peer access.  Either way every rank
+ends up with the full image.
 
 The layout helpers are plain numpy (host logic, covered by world_size-2 gloo tests on CPU); on
 the GPU the pack / unpack are CUDA kernels behind swr_pack_tiles / swr_unpack_tiles.
@@ -263,10 +266,14 @@ class ReplicatedUpload:
         self.full = torch.empty(self.per * world, dtype=torch.uint8, device=device)
         self.h2d_bytes = self.per                       # per rank and step
 
-    def run(self):
-        """Enqueue on torch's current stream; returns the device address of each array."""
+    def run(self, h2d_done=None):
+        """Enqueue on torch's current stream; returns the device address of each array.  `h2d_done` (a CUDA event) is
+        recorded between the PCIe copy and the all-gather: other host -> device copies of the step can wait for it on
+        a stream of their own and then run under the all-gather (PCIe and NVLink are independent)."""
         import torch.distributed as dist
         self.slice_dev.copy_(self.slice_host, non_blocking=True)
+        if h2d_done is not None:
+            h2d_done.record()
         dist.all_gather_into_tensor(self.full, self.slice_dev, group=self.group)
         base = self.full.data_ptr()
         return [base + off for off in self.offsets]

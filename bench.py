@@ -543,6 +543,8 @@ def bench_workload(args, workload, steps, warmup, rank, local_rank, world, dev, 
         if ms_e2e is not None:
             res["e2e"] = {"value": fragments / (ms_e2e / steps * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / steps,
                           "host_enqueue_ms_per_step": host_e2e,
+                          "host_binding": (f"each rank runs on the {len(args.numa_cpus)} CPUs next to its GPU (NVML affinity), its staging buffers are local to that socket"
+                                           if getattr(args, "numa_cpus", None) else "none"),
                           "h2d_bytes_per_step": int(in_bytes) if world == 1 else int((repl[0].h2d_bytes + (own_runs.numel() * 4 if own_runs is not None else 0)) * world),
                           "d2h_bytes_per_step": int(W * H * 4),
                           "path": "host buffers -> swr_draw_elements (staged by the library, indices streamed pass by pass) -> frame to host" if world == 1 else
@@ -572,6 +574,26 @@ def bench_workload(args, workload, steps, warmup, rank, local_rank, world, dev, 
     return res
 
 
+def bind_to_gpu_numa_node(torch, local_rank):
+    """One process per GPU: run on the CPUs next to this process's GPU, so that the page-locked staging buffers it
+    allocates (first touch) sit in the memory of that socket and its host <-> device copies do not cross the socket
+    interconnect.  With 8 ranks uploading at once that link, not PCIe, is what saturates.  Best effort: returns the
+    CPU set it bound to, or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        p = torch.cuda.get_device_properties(local_rank)
+        bus = f"{p.pci_domain_id:08x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        cpus = sorted(os.sched_getaffinity(0))
+        print(f"[bench] rank on GPU {local_rank} ({bus}) bound to {len(cpus)} CPUs {cpus[0]}..{cpus[-1]}", file=sys.stderr)
+        return cpus
+    except Exception as e:                            # noqa: BLE001
+        print(f"[bench] NUMA binding skipped: {e}", file=sys.stderr)
+        return None
+
+
 def run_gpu_arm(args):
     # NCCL and friends write banners straight to fd 1; the contract is ONE JSON line on stdout, so
     # everything else is sent to stderr and the line goes to the saved descriptor at the end.
@@ -586,6 +608,7 @@ def run_gpu_arm(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    args.numa_cpus = bind_to_gpu_numa_node(torch, local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 

@@ -22,6 +22,14 @@ for tile in (32, 64):
         out = sr.render(sc)
         print(tile, sc.name, out["fragments"], flush=True)
         sr.close()
+# heavy-tile split: every busy tile shaded by four quadrant CTAs
+for tile in (32, 64):
+    for sc in (cases[0], cases[2], cases[3]):
+        sr = SceneRenderer(sc.width, sc.height, tile_size=tile)
+        sr.r.setTileSplit(1)
+        out = sr.render(sc)
+        print("split", tile, sc.name, out["fragments"], flush=True)
+        sr.close()
 # sharded geometry: two contexts on this GPU push records into each other's scratch, ordered by the flag barrier
 sc = S.config_c3(120, 100, 320, 200)
 srs = [SceneRenderer(sc.width, sc.height) for _ in range(2)]

@@ -485,8 +485,10 @@ def bench_workload(args, workload, steps, warmup, rank, local_rank, world, dev, 
     if with_cpu is not None:
         for _ in range(2):
             step_e2e()
+        r.resetStats()
         ms_e2e = timed(step_e2e, steps)
         host_e2e = host_ms["last"]
+        h2d_lib = int(r.stats().h2d_bytes) // max(1, steps)       # what the library's staging really copied per step
         if frame_shared is not None:
             # the bands of all ranks make up the frame rank 0 holds on its device
             same = torch.tensor([1], dtype=torch.int32, device=dev)
@@ -542,12 +544,16 @@ def bench_workload(args, workload, steps, warmup, rank, local_rank, world, dev, 
         }
         if ms_e2e is not None:
             res["e2e"] = {"value": fragments / (ms_e2e / steps * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / steps,
-                          "host_enqueue_ms_per_step": host_e2e,
+                          "host_enqueue_ms_per_step": host_e2e,       # host time inside the calls of a step: enqueueing, packing the
+                                                                      # index slices, and waiting for a staging set of two steps ago
                           "host_binding": (f"each rank runs on the {len(args.numa_cpus)} CPUs next to its GPU (NVML affinity), its staging buffers are local to that socket"
                                            if getattr(args, "numa_cpus", None) else "none"),
-                          "h2d_bytes_per_step": int(in_bytes) if world == 1 else int((repl[0].h2d_bytes + (own_runs.numel() * 4 if own_runs is not None else 0)) * world),
+                          "h2d_bytes_per_step": int(h2d_lib) if world == 1 else int((repl[0].h2d_bytes + (own_runs.numel() * 4 if own_runs is not None else 0)) * world),
                           "d2h_bytes_per_step": int(W * H * 4),
-                          "path": "host buffers -> swr_draw_elements (staged by the library, indices streamed pass by pass) -> frame to host" if world == 1 else
+                          "input_bytes_per_step": int(in_bytes),
+                          "path": ("host buffers -> swr_draw_elements (staged by the library, indices streamed pass by pass"
+                                   + (", slices of local indices packed to 16 bits + block bases by host threads and widened on the device" if h2d_lib < in_bytes else "")
+                                   + ") -> frame to host") if world == 1 else
                                   ((f"each rank uploads 1/{world} of the vertices (NCCL all-gather replicates them) and the index runs of its own batches"
                                     + (" (under the all-gather)" if idx_stream is not None else "") if shards is not None else
                                     f"each rank uploads 1/{world} of the geometry, NCCL all-gather replicates it") + ", draw + composite, "

@@ -132,6 +132,15 @@ SWR_API int swr_set_uniforms(swr_context *ctx, const void *data, size_t bytes);
  * screen tiles t with (tx + 3*ty) % world == rank (geometry is processed in full). */
 SWR_API int swr_set_tile_size(swr_context *ctx, int tile_size);
 SWR_API int swr_set_tile_partition(swr_context *ctx, int rank, int world);
+/* Host index arrays of big draws (>= 32 MB, uploaded slice by slice under the kernels): a slice whose blocks of 4096
+ * consecutive indices each span at most 65535 vertices is sent as 16-bit offsets + one 32-bit base per block (packed by
+ * a few host threads while the previous slice is on the link) and widened on the device -- lossless, half the bytes.
+ * mode -1 = automatic (kept while this host packs faster than ~32 GB/s, i.e. faster than PCIe would have carried the
+ * saved bytes), 0 = off, 1 = always try.  The reference passes the same int32 array (VertexProcessor.h:90). */
+SWR_API int swr_set_index_narrowing(swr_context *ctx, int mode);
+/* test hook (no GPU needed): the host-side packer; returns 1 = packed, 0 = some block spans more than 16 bits,
+ * -1 = this CPU has no AVX2 (narrowing is then never used).  bases needs ceil(count / 4096) entries. */
+SWR_API int swr_debug_pack_indices16(const int32_t *indices, size_t count, uint16_t *offsets, int32_t *bases);
 /* Heavy-tile split: a tile whose binning pass lists more than `groups` 32-record groups is shaded by four CTAs, one
  * per quadrant (results are unchanged: every pixel still sees its fragments in emission order).  -1 = automatic
  * (currently off: on the measured meshes the repeated record tests cost more than the shorter tail saves), 0 = off.
@@ -182,6 +191,7 @@ typedef struct swr_stats {
     int32_t last_tile_size;
     int32_t reserved;
     uint64_t scratch_bytes;
+    uint64_t h2d_bytes;          /* bytes the library's staging copied host -> device (vertex attributes, indices) */
 } swr_stats;
 SWR_API int swr_get_stats(swr_context *ctx, swr_stats *out);   /* synchronizes the stream */
 SWR_API int swr_reset_stats(swr_context *ctx);

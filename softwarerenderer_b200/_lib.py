@@ -19,7 +19,7 @@ class SwrStats(C.Structure):
         ("fragments", C.c_uint64), ("primitives_in", C.c_uint64), ("kernel_launches", C.c_uint64),
         ("draws", C.c_uint64), ("passes", C.c_uint64),
         ("last_geometry_ms", C.c_float), ("last_tile_ms", C.c_float),
-        ("last_tile_size", C.c_int32), ("reserved", C.c_int32), ("scratch_bytes", C.c_uint64),
+        ("last_tile_size", C.c_int32), ("reserved", C.c_int32), ("scratch_bytes", C.c_uint64), ("h2d_bytes", C.c_uint64),
     ]
 
 
@@ -51,6 +51,8 @@ SYMBOLS = [
     ("swr_set_uniforms", C.c_int, [_P, _P, C.c_size_t]),
     ("swr_set_tile_size", C.c_int, [_P, C.c_int]),
     ("swr_set_tile_split", C.c_int, [_P, C.c_int]),
+    ("swr_set_index_narrowing", C.c_int, [_P, C.c_int]),
+    ("swr_debug_pack_indices16", C.c_int, [_P, C.c_size_t, _P, _P]),
     ("swr_set_tile_partition", C.c_int, [_P, C.c_int, C.c_int]),
     ("swr_set_scratch_limit", C.c_int, [_P, C.c_size_t]),
     ("swr_set_stream", C.c_int, [_P, _P]),

@@ -122,6 +122,10 @@ class Rasterizer:
     def setTileSize(self, tile: int):
         _lib.check(lib.swr_set_tile_size(self._ctx, tile), "setTileSize")
 
+    def setIndexNarrowing(self, mode: int):
+        """Narrowed upload of big host index arrays (-1 automatic, 0 off, 1 always try); see swr_set_index_narrowing."""
+        _lib.check(lib.swr_set_index_narrowing(self._ctx, mode), "setIndexNarrowing")
+
     def setTileSplit(self, groups: int):
         """Heavy-tile split threshold in listed 32-record groups (-1 automatic, 0 off); see swr_set_tile_split."""
         _lib.check(lib.swr_set_tile_split(self._ctx, groups), "setTileSplit")

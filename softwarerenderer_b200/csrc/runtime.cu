@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -43,6 +44,39 @@ int fail(int code, const char *fmt, ...)
         cudaError_t e__ = (expr);                                                                  \
         if (e__ != cudaSuccess) return fail(-100, "%s: %s", #expr, cudaGetErrorString(e__));       \
     } while (0)
+
+// hostpack.cpp (g++ -mavx2): the host side of the narrowed index upload
+extern "C" {
+void *swr_hostpack_create(int workers);
+void swr_hostpack_destroy(void *pool);
+int swr_hostpack_pack16(void *pool, const int32_t *src, size_t count, uint16_t *dst16, int32_t *bases);
+}
+constexpr size_t kIdxBlock = 4096;         // indices per base of the narrowed form (hostpack.cpp: kBlock)
+
+struct HostBuf {                           // page-locked host memory, grow-only
+    void *ptr = nullptr;
+    size_t bytes = 0;
+    int reserve(size_t need)
+    {
+        if (need <= bytes) return 0;
+        if (ptr) cudaFreeHost(ptr);
+        ptr = nullptr;
+        bytes = 0;
+        const cudaError_t e = cudaMallocHost(&ptr, need);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(-102, "cudaMallocHost(%zu bytes): %s", need, cudaGetErrorString(e));
+        }
+        bytes = need;
+        return 0;
+    }
+    void release()
+    {
+        if (ptr) cudaFreeHost(ptr);
+        ptr = nullptr;
+        bytes = 0;
+    }
+};
 
 struct DevBuf {
     void *ptr = nullptr;
@@ -216,6 +250,14 @@ struct swr_context {
     cudaEvent_t stageFree[2] = { nullptr, nullptr };   // recorded after the last kernel of the draw that last read the set
     bool stageUsed[2] = { false, false };
     int stageSet = 0;
+    // narrowed index upload of streamed draws (hostpack.cpp): per staging set the packed form in page-locked host
+    // memory and its device copy; layout of both: 16-bit offsets of the whole draw, then one int32 base per block
+    void *packPool = nullptr;
+    HostBuf pack16[2];
+    DevBuf dev16[2];
+    int narrowMode = -1;                // -1 automatic (by the measured packing rate), 0 off, 1 always try
+    double packGBps = 0.0;              // best packing rate of a draw so far (source bytes / host time)
+    int packDraws = 0;                  // draws that measured it
     uint32_t *hostFlags = nullptr;   // pinned: error flag read-back
     int lastDrawMode = 0;
 
@@ -235,7 +277,7 @@ size_t scratchBytes(const swr_context *c)
     size_t n = c->sets[0].bytes() + c->sets[1].bytes() + c->arena.bytes + c->stageIdx.bytes + c->l2flush.bytes + c->ownedIdx.bytes +
                c->soVerts.bytes + c->soIndices.bytes + c->soCounts.bytes;
     for (int i = 0; i < SWR_MAX_VERTEX_ATTRIBS; ++i) n += c->stageAttrib[i].bytes + c->stageAttribB[i].bytes;
-    n += c->stageIdxB.bytes;
+    n += c->stageIdxB.bytes + c->dev16[0].bytes + c->dev16[1].bytes;
     return n;
 }
 
@@ -403,6 +445,27 @@ int enqueuePeerBarrier(swr_context *c)
     return 0;
 }
 
+// Narrowed index upload: out[i] = bases[i / 4096] + offsets[i] (see hostpack.cpp).  Eight indices per thread: one
+// 16-byte read, two 16-byte writes; `offsets` and `out` are 32-byte aligned (slices start at multiples of 1024 primitives).
+__global__ void widenIndicesKernel(const uint16_t *offsets, const int32_t *bases, int32_t *out, size_t count)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t n8 = count / 8;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n8; t += stride) {
+        const uint4 v = reinterpret_cast<const uint4 *>(offsets)[t];
+        const int32_t b = bases[(t * 8) / kIdxBlock];
+        int4 lo, hi;
+        lo.x = b + (int)(v.x & 0xffffu); lo.y = b + (int)(v.x >> 16); lo.z = b + (int)(v.y & 0xffffu); lo.w = b + (int)(v.y >> 16);
+        hi.x = b + (int)(v.z & 0xffffu); hi.y = b + (int)(v.z >> 16); hi.z = b + (int)(v.w & 0xffffu); hi.w = b + (int)(v.w >> 16);
+        reinterpret_cast<int4 *>(out)[2 * t] = lo;
+        reinterpret_cast<int4 *>(out)[2 * t + 1] = hi;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (count & 7)) {
+        const size_t i = n8 * 8 + threadIdx.x;
+        out[i] = bases[i / kIdxBlock] + (int)offsets[i];
+    }
+}
+
 __global__ void maxIndexKernel(const int32_t *idx, size_t n, int *out)
 {
     int m = -1;
@@ -492,7 +555,10 @@ int drawCommon(swr_context *c, int drawMode, size_t count, const int32_t *indice
     if (streamIdx && c->stageUsed[S]) CUDA_TRY(cudaStreamWaitEvent(hs, c->stageFree[S], 0));   // kernels of the draw that last read this set
     if (!idxOnDevice) {
         if (int rc = stageIdx.reserve(count * sizeof(int32_t))) return rc;
-        if (!streamIdx) CUDA_TRY(cudaMemcpyAsync(stageIdx.ptr, indices, idxBytes, cudaMemcpyHostToDevice, gs));
+        if (!streamIdx) {
+            CUDA_TRY(cudaMemcpyAsync(stageIdx.ptr, indices, idxBytes, cudaMemcpyHostToDevice, gs));
+            c->stats.h2d_bytes += idxBytes;
+        }
         devIndices = static_cast<const int32_t *>(stageIdx.ptr);
         staged = true;
     }
@@ -502,6 +568,7 @@ int drawCommon(swr_context *c, int drawMode, size_t count, const int32_t *indice
             const size_t bytes = rasterVertCount * 144;
             if (int rc = stageAttrib[0].reserve(bytes)) return rc;
             CUDA_TRY(cudaMemcpyAsync(stageAttrib[0].ptr, rasterVerts, bytes, cudaMemcpyHostToDevice, gs));
+            c->stats.h2d_bytes += bytes;
             dv = stageAttrib[0].ptr;
             staged = true;
         }
@@ -524,6 +591,7 @@ int drawCommon(swr_context *c, int drawMode, size_t count, const int32_t *indice
                 }
                 if (int rc = stageAttrib[i].reserve(bytes)) return rc;
                 CUDA_TRY(cudaMemcpyAsync(stageAttrib[i].ptr, a.ptr, bytes, cudaMemcpyHostToDevice, hs));
+                c->stats.h2d_bytes += bytes;
                 dp = stageAttrib[i].ptr;
                 staged = true;
             }
@@ -696,12 +764,63 @@ int drawCommon(swr_context *c, int drawMode, size_t count, const int32_t *indice
             CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
             c->idxReady.push_back(ev);
         }
-        size_t k = 0;
+        // Narrowed upload (hostpack.cpp): a slice whose blocks of 4096 indices each span at most 65535 vertices crosses
+        // PCIe as 16-bit offsets + one base per block and is widened on the device; the host threads pack slice k + 1
+        // while slice k (and, before the first one, the vertex attributes) are on the link.  Automatic mode keeps it
+        // only where the host packs faster than the link would have carried the saved bytes.
+        int narrow = c->narrowMode;
+        if (const char *env = getenv("SWR_INDEX_NARROWING")) narrow = atoi(env);
+        if (narrow < 0) {
+            const char *env = getenv("SWR_NARROW_MIN_GBPS");
+            narrow = (c->packDraws < 3 || c->packGBps >= (env ? atof(env) : 32.0)) ? 1 : 0;   // judged by the best of the first draws
+        }
+        if (narrow && !__builtin_cpu_supports("avx2")) narrow = 0;
+        uint16_t *h16 = nullptr, *d16 = nullptr;
+        int32_t *hBase = nullptr, *dBase = nullptr;
+        if (narrow) {
+            const size_t nIdx = nprims * per, nBlocksMax = nIdx / kIdxBlock + npass + 1;
+            const size_t baseOfs = (nIdx * 2 + 255) / 256 * 256;
+            if (int rc = c->pack16[S].reserve(baseOfs + nBlocksMax * 4)) return rc;
+            if (int rc = c->dev16[S].reserve(baseOfs + nBlocksMax * 4)) return rc;
+            if (!c->packPool) c->packPool = swr_hostpack_create(-1);
+            // the copies that last read this set's host buffer belong to a draw whose kernels stageFree[S] follows
+            if (c->stageUsed[S]) CUDA_TRY(cudaEventSynchronize(c->stageFree[S]));
+            h16 = static_cast<uint16_t *>(c->pack16[S].ptr);
+            d16 = static_cast<uint16_t *>(c->dev16[S].ptr);
+            hBase = reinterpret_cast<int32_t *>(static_cast<char *>(c->pack16[S].ptr) + baseOfs);
+            dBase = reinterpret_cast<int32_t *>(static_cast<char *>(c->dev16[S].ptr) + baseOfs);
+        }
+        size_t k = 0, blockAt = 0;
+        double packSec = 0.0, packBytes = 0.0;
         for (size_t first = 0; first < nprims; first += passPrims, ++k) {
             const size_t n = std::min(passPrims, nprims - first);
-            CUDA_TRY(cudaMemcpyAsync(static_cast<int32_t *>(stageIdx.ptr) + first * per, indices + first * per, n * per * sizeof(int32_t),
-                                     cudaMemcpyHostToDevice, hs));
+            const size_t at = first * per, cnt = n * per;
+            bool narrowed = false;
+            if (narrow) {
+                const size_t nb = (cnt + kIdxBlock - 1) / kIdxBlock;
+                const auto t0 = std::chrono::steady_clock::now();
+                narrowed = swr_hostpack_pack16(c->packPool, indices + at, cnt, h16 + at, hBase + blockAt) != 0;
+                const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+                packSec += sec;
+                if (narrowed) {
+                    packBytes += (double)cnt * 4.0;
+                    CUDA_TRY(cudaMemcpyAsync(d16 + at, h16 + at, cnt * 2, cudaMemcpyHostToDevice, hs));
+                    CUDA_TRY(cudaMemcpyAsync(dBase + blockAt, hBase + blockAt, nb * 4, cudaMemcpyHostToDevice, hs));
+                    widenIndicesKernel<<<148 * 4, 256, 0, hs>>>(d16 + at, dBase + blockAt, static_cast<int32_t *>(stageIdx.ptr) + at, cnt);
+                    c->stats.kernel_launches++;
+                    c->stats.h2d_bytes += cnt * 2 + nb * 4;
+                    blockAt += nb;
+                }
+            }
+            if (!narrowed) {
+                CUDA_TRY(cudaMemcpyAsync(static_cast<int32_t *>(stageIdx.ptr) + at, indices + at, cnt * sizeof(int32_t), cudaMemcpyHostToDevice, hs));
+                c->stats.h2d_bytes += cnt * sizeof(int32_t);
+            }
             CUDA_TRY(cudaEventRecord(c->idxReady[k], hs));
+        }
+        if (narrow && packSec > 0.0) {                     // source bytes packed per second of this draw (failed slices count as time only)
+            c->packGBps = std::max(c->packGBps, packBytes / packSec * 1e-9);
+            c->packDraws++;
         }
     }
     CUDA_TRY(cudaEventRecord(c->evGeom0, gs));
@@ -877,6 +996,8 @@ void swr_destroy(swr_context *c)
     for (int i = 0; i < SWR_MAX_VERTEX_ATTRIBS; ++i) c->stageAttrib[i].release();
     for (auto &o : c->ipcOpened) cudaIpcCloseMemHandle(o.second);
     if (c->hostFlags) cudaFreeHost(c->hostFlags);
+    if (c->packPool) swr_hostpack_destroy(c->packPool);
+    for (int i = 0; i < 2; ++i) { c->pack16[i].release(); c->dev16[i].release(); }
     cudaEvent_t evs[] = { c->evGeom0, c->evGeom1, c->evTile0, c->evTile1, c->evTimer0, c->evTimer1, c->evDrawStart,
                           c->sets[0].geomDone, c->sets[0].tileDone, c->sets[1].geomDone, c->sets[1].tileDone, c->stageFree[0], c->stageFree[1] };
     for (cudaEvent_t ev : evs)
@@ -989,6 +1110,24 @@ int swr_set_tile_size(swr_context *c, int tile_size)
     if (tile_size != c->tileSizeReq) c->pinnedTileShift = 0;
     c->tileSizeReq = tile_size;
     return 0;
+}
+
+int swr_set_index_narrowing(swr_context *c, int mode)
+{
+    if (!c) return fail(-1, "null context");
+    if (mode < -1 || mode > 1) return fail(-2, "index narrowing mode must be -1 (automatic), 0 (off) or 1 (always try)");
+    c->narrowMode = mode;
+    return 0;
+}
+
+int swr_debug_pack_indices16(const int32_t *indices, size_t count, uint16_t *offsets, int32_t *bases)
+{
+    if (!indices || !offsets || !bases) return fail(-1, "null argument");
+    if (!__builtin_cpu_supports("avx2")) return -1;
+    void *pool = swr_hostpack_create(3);
+    const int ok = swr_hostpack_pack16(pool, indices, count, offsets, bases);
+    swr_hostpack_destroy(pool);
+    return ok;
 }
 
 int swr_set_tile_split(swr_context *c, int groups)

@@ -84,3 +84,42 @@ def test_scene_generators_shapes():
     assert e.tolist() == [0, 1, 1, 2, 2, 0, 3, 4, 4, 5, 5, 3]
     v, i = S.benchmark_mesh(4)
     assert v.shape == (12, 6) and i.tolist() == list(range(12))
+
+
+def test_index_narrowing_host_packer_round_trip():
+    """hostpack.cpp (the host side of the narrowed index upload): base per block of 4096 + 16-bit offsets reproduce the
+    indices exactly; a block that spans more than 65535 vertices makes the slice fall back to the plain copy."""
+    from softwarerenderer_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(7)
+
+    def pack(idx):
+        idx = np.ascontiguousarray(idx, dtype=np.int32)
+        off = np.zeros(max(1, idx.size), dtype=np.uint16)
+        bases = np.full((idx.size + 4095) // 4096 + 1, -7, dtype=np.int32)
+        rc = lib.swr_debug_pack_indices16(idx.ctypes.data, idx.size, off.ctypes.data, bases.ctypes.data)
+        return rc, off[:idx.size], bases
+
+    rc, _, _ = pack(np.arange(10))
+    if rc == -1:
+        pytest.skip("no AVX2 on this CPU: the library never narrows")
+    for n in (1, 7, 8, 15, 16, 17, 4095, 4096, 4097, 12288, 100003, 1 << 20):
+        # a mesh-like stream: a slowly moving window of 60000 vertices, far above 2^16 in absolute value
+        centre = 3_000_000 + (np.arange(n) // 3) * 2
+        idx = (centre + rng.integers(0, 60000, n)).astype(np.int32)
+        rc, off, bases = pack(idx)
+        assert rc == 1, n
+        nb = (n + 4095) // 4096
+        assert bases[nb] == -7                                          # nothing written past the last block
+        want_base = np.array([idx[b * 4096:(b + 1) * 4096].min() for b in range(nb)], dtype=np.int32)
+        assert np.array_equal(bases[:nb], want_base)
+        assert np.array_equal(np.repeat(bases[:nb], 4096)[:n] + off.astype(np.int32), idx)
+    # the limit: a span of exactly 65535 still fits, 65536 does not (in any position of any block)
+    idx = np.full(9000, 1000, dtype=np.int32)
+    idx[4100] = 1000 + 65535
+    assert pack(idx)[0] == 1
+    for pos in (0, 4095, 4096, 8999):
+        bad = np.full(9000, 1000, dtype=np.int32)
+        bad[pos] = 1000 + 65536 if pos else 1000 - 65536
+        assert pack(bad)[0] == 0, pos
+    assert pack(np.array([-5, 7, 65530 - 5], dtype=np.int32))[0] == 1   # negative (invalid) indices must not break the packer

@@ -170,6 +170,39 @@ def test_streamed_host_indices(oracle):
     sr.close()
 
 
+def test_streamed_host_indices_narrowed_and_not(oracle):
+    """The narrowed upload of streamed host indices (16-bit offsets + block bases, widened on the device) is lossless:
+    forced on, forced off, and on index streams whose slices cannot be narrowed (shuffled triangle order: a block of
+    4096 indices spans the whole vertex range) or only partly (first half in mesh order, second half shuffled)."""
+    from softwarerenderer_b200.api import SceneRenderer
+    base = S.config_c3(1300, 1100, 960, 540, ps=S.PS_COUNT_ID)
+    tris = base.indices.reshape(-1, 3)
+    rng = np.random.default_rng(3)
+    half = int(tris.shape[0] * 0.6)          # the first slice (half of the draw) stays in mesh order, the second does not
+    shuffled = tris[rng.permutation(tris.shape[0])]
+    mixed = np.concatenate([tris[:half], tris[half:][rng.permutation(tris.shape[0] - half)]])
+    raw_bytes = base.vertices.nbytes + base.indices.nbytes
+    for label, idx, modes in (("mesh", tris, (1, 0, -1)), ("shuffled", shuffled, (1,)), ("mixed", mixed, (1,))):
+        scene = base.replace(indices=np.ascontiguousarray(idx.reshape(-1)))
+        want = oracle.run(scene, "oracle")
+        for mode in modes:
+            sr = SceneRenderer(scene.width, scene.height)
+            sr.r.setIndexNarrowing(mode)
+            for rep in range(2):
+                sr.r.resetStats()
+                got = sr.render(scene)
+                assert got["stats"].passes >= 2
+                check(got, want, f"narrow_{label}_mode{mode}_{rep}")
+                h2d = int(got["stats"].h2d_bytes)
+                if label == "mesh" and mode == 1:
+                    assert h2d < raw_bytes - scene.indices.nbytes // 2 + (1 << 20), (h2d, raw_bytes)     # indices at half size
+                if mode == 0 or label == "shuffled":
+                    assert h2d == raw_bytes, (h2d, raw_bytes)
+                if label == "mixed":
+                    assert raw_bytes - scene.indices.nbytes // 2 < h2d < raw_bytes, (h2d, raw_bytes)
+            sr.close()
+
+
 def test_device_resident_inputs(oracle, renderers):
     """Vertex / index buffers already in HBM are used in place."""
     scene = S.config_c2(100, 50, 480, 270)

@@ -173,7 +173,7 @@ def run_reference_arm(args):
     if rank != 0:
         return
     scene, b_frag, wl = make_scene(args.workload)
-    budget = 150.0
+    budget = args.ref_budget
     per_step = budget / max(1, args.steps + args.warmup)
     fps, tps, desc, t = cpu_reference_rate(scene, budget_s=per_step * max(1, args.steps), steps=max(1, args.steps))
     line = {
@@ -655,6 +655,7 @@ def main():
                     help="N>1: vertex stage sharded by batches with records pushed to the tile owners (default) or run in full by every rank")
     ap.add_argument("--scratch-gb", type=float, default=0.0, help="N>1, sharded geometry: size of the shared scratch arena per rank (0 = by workload)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--ref-budget", type=float, default=150.0, help="--impl reference: seconds of CPU work for the whole run (bounded sample of the workload)")
     ap.add_argument("--also", default="", help="comma-separated further workloads measured with a few steps into line['also'] (default: c5 when N > 1); 'none' for none")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

@@ -8,6 +8,8 @@ import pytest
 import common
 from softwarerenderer_b200 import present, scenes as S
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
 QUAD_OBJ = """
 # one quad and one triangle sharing an edge
 v 0 0 0
@@ -73,3 +75,26 @@ def test_scene_generators_have_the_named_shapes():
     assert e.tolist() == [0, 1, 1, 2, 2, 0]
     d = S.dotnet_random_doubles(0, 3)
     assert abs(d[0] - 0.7262432699679598) < 1e-15            # Random(0).NextDouble(), Random.cpp:7-50
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the arm the driver runs next to the GPU arm): ONE JSON line on stdout with the
+    contract's keys, measured on the reference build (or the oracle port) -- here with a one-second budget."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "c0", "--steps", "1",
+                          "--warmup", "0", "--ref-budget", "1"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, out.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "shaded_fragments_per_s" and d["unit"] == "fragments/s"
+    for k in ("value", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config"):
+        assert k in d, k
+    assert d["value"] > 0 and d["higher_is_better"] is True and d["vs_baseline"] is None and d["dtype"] == "f32"
+    assert "Benchmark.cpp" in d["config"]["workload"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] == 1 and cb["value"] == d["value"] and "primitives" in cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["gpu_launches"] == 0

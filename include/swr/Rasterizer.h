@@ -116,6 +116,7 @@ public:
     /// Multi-GPU, one process per GPU (sort-first): this context shades the screen tiles of `rank` out of `world`.
     void setTilePartition(int rank, int world) { detail::check(swr_set_tile_partition(m_ctx, rank, world), "setTilePartition"); }
     void setTileSplit(int groups) { detail::check(swr_set_tile_split(m_ctx, groups), "setTileSplit"); }      // heavy tiles shaded by four CTAs
+    void setIndexNarrowing(int mode) { detail::check(swr_set_index_narrowing(m_ctx, mode), "setIndexNarrowing"); }   // big host index arrays as 16-bit offsets over PCIe
     /// ... and stores every finished tile of `slot` also into `count` peer surfaces (mapped with swr_ipc_open): the
     /// composite then needs no pass of its own, only a cross-rank barrier after the draws (see swr_b200.h).
     void setTileMirrors(int slot, int count, void *const *surfaces)
